@@ -1,0 +1,91 @@
+"""ctypes binding of libvq_b200.so (C ABI declared in include/vq_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libvq_b200.so"
+
+VQ_BF16, VQ_F32 = 0, 1
+EPI_LINEAR, EPI_GELU, EPI_GELU_BWD, EPI_QKV_ROPE, EPI_PATCH = 0, 1, 2, 3, 4
+
+_f32p = C.c_void_p
+
+
+class GemmDesc(C.Structure):
+    """Mirror of `vq_gemm_desc` (include/vq_b200.h)."""
+
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("a_major", C.c_int32), ("b_major", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("B", C.c_void_p), ("ldb", C.c_int64),
+        ("C", C.c_void_p), ("ldc", C.c_int64),
+        ("c_dtype", C.c_int32),
+        ("Z0", C.c_int32), ("Z1", C.c_int32),
+        ("a_r0", C.c_int64), ("a_c0", C.c_int64), ("a_r1", C.c_int64), ("a_c1", C.c_int64),
+        ("b_r0", C.c_int64), ("b_c0", C.c_int64), ("b_r1", C.c_int64), ("b_c1", C.c_int64),
+        ("c_r0", C.c_int64), ("c_c0", C.c_int64), ("c_r1", C.c_int64), ("c_c1", C.c_int64),
+        ("a_rows", C.c_int64), ("a_cols", C.c_int64), ("b_rows", C.c_int64), ("b_cols", C.c_int64),
+        ("epilogue", C.c_int32),
+        ("alpha", C.c_float),
+        ("bias", _f32p), ("gamma", _f32p),
+        ("add", C.c_void_p), ("ldadd", C.c_int64),
+        ("aux", C.c_void_p), ("ldaux", C.c_int64),
+        ("tokens_per_frame", C.c_int32), ("patch_start", C.c_int32), ("grid_w", C.c_int32),
+        ("apply_qknorm_rope", C.c_int32),
+        ("qn_w", _f32p), ("qn_b", _f32p), ("kn_w", _f32p), ("kn_b", _f32p),
+        ("qk_eps", C.c_float), ("q_scale", C.c_float),
+        ("rope_cos", _f32p), ("rope_sin", _f32p),
+        ("n_patches", C.c_int32),
+        ("pos_embed", _f32p),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib: C.CDLL) -> None:
+    lib.vq_last_error.restype = C.c_char_p
+    lib.vq_last_error.argtypes = []
+    lib.vq_version.restype = C.c_int
+    lib.vq_num_sms.restype = C.c_int
+    lib.vq_gemm.restype = C.c_int
+    lib.vq_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    lib.vq_attention_fwd.restype = C.c_int
+    lib.vq_attention_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    for name, argtypes in _EXTRA_DECLS.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+
+
+# name -> argtypes for the row/elementwise entry points (all return int status)
+_i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+_EXTRA_DECLS: dict[str, list] = {}
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the C-ABI library. Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m vggt_qwen3_b200.csrc.build` "
+                "(there is no CPU / PyTorch fallback for this path)"
+            )
+        handle = C.CDLL(os.fspath(LIB_PATH))
+        _declare(handle)
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().vq_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with status {status}: {msg}")

@@ -1,0 +1,83 @@
+"""Build libvq_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+Usage:  python -m vggt_qwen3_b200.csrc.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent
+LIB_PATH = CSRC.parent / "libvq_b200.so"
+STAMP = CSRC.parent / ".libvq_b200.stamp"
+SOURCES = ["common.cu", "gemm.cu", "attention.cu", "rowops.cu", "perceiver_ops.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; libvq_b200.so cannot be built")
+
+
+def _sources() -> list[Path]:
+    return [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    for p in sorted(CSRC.glob("*.cu*")) + [CSRC.parent.parent / "include" / "vq_b200.h"]:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    fp = _fingerprint()
+    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == fp:
+        return LIB_PATH
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    build_dir = CSRC.parent / "build"
+    build_dir.mkdir(exist_ok=True)
+    for src in _sources():
+        obj = build_dir / (src.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+            print(" ".join(cmd), flush=True)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- nvcc failed for {src.name} ---\n{out}\n")
+        elif verbose and out:
+            print(f"--- {src.name} ---\n{out}")
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    link = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
+    subprocess.run(link, check=True)
+    STAMP.write_text(fp)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

@@ -1,0 +1,41 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and the TMA descriptor cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/vq_b200.h"
+
+namespace vq {
+
+void set_error(const std::string& msg);
+
+#define VQ_CHECK_ARG(cond, msg)                                  \
+  do {                                                           \
+    if (!(cond)) {                                               \
+      ::vq::set_error(std::string("invalid argument: ") + (msg)); \
+      return VQ_ERR_INVALID;                                     \
+    }                                                            \
+  } while (0)
+
+#define VQ_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::vq::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));            \
+      return VQ_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+// 2-D bf16 tensor map with SWIZZLE_128B.  `inner`/`outer` are the tensor extents in elements,
+// `ld` the row pitch in elements, box = {box_inner (must be 64), box_outer}.
+// Returns nullptr (and sets the error string) on failure.  Descriptors are cached for the life of
+// the process, keyed by every argument; they are immutable.
+const CUtensorMap* get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                                    uint32_t box_inner, uint32_t box_outer);
+
+int num_sms();
+
+}  // namespace vq

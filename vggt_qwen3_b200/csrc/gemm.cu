@@ -1,0 +1,530 @@
+// vq_gemm: persistent, warp-specialised bf16 GEMM on the 5th-gen tensor cores (sm_100a).
+//
+//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B boxes) -> smem ring, mbarrier full/empty
+//   warp 1      MMA issuer     one lane issues tcgen05.mma (128 x BLOCK_N x 16) into a double-buffered
+//                              TMEM accumulator; tcgen05.commit releases smem stages / publishes tiles
+//   warps 2..5  epilogue       tcgen05.ld (one accumulator row per thread) -> fused epilogue -> global
+//
+// Both operands may be K-major or MN-major (UMMA descriptor + instruction-descriptor major bits), so the
+// same kernel serves forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without materialised transposes.
+#include <math.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vq {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+
+struct GemmArgs {
+  int M, N, K;
+  int a_mn, b_mn;
+  int Z1;            // inner batch extent (z = z0 * Z1 + z1)
+  int m_tiles, n_tiles, total_tiles;
+  int a_r0, a_c0, a_r1, a_c1;
+  int b_r0, b_c0, b_r1, b_c1;
+  long long c_r0, c_c0, c_r1, c_c1;
+  void* C;
+  long long ldc;
+  float alpha;
+  const float* bias;
+  const float* gamma;
+  const void* add;
+  long long ldadd;
+  void* aux;
+  long long ldaux;
+  // QKV_ROPE / PATCH
+  int tokens_per_frame, patch_start, grid_w, apply_qknorm_rope;
+  const float *qn_w, *qn_b, *kn_w, *kn_b;
+  float qk_eps, q_scale;
+  const float *rope_cos, *rope_sin;
+  int n_patches;
+  const float* pos_embed;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 / 512)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <bool F32>
+__device__ __forceinline__ void store8(void* base, long long off, const float* v) {
+  if constexpr (F32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]);
+    u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]);
+    u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = u;
+  }
+}
+template <bool F32>
+__device__ __forceinline__ void load8(const void* base, long long off, float* v) {
+  if constexpr (F32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+    v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x);
+    v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z);
+    v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+  }
+}
+
+// MODE: VQ_EPI_* ; OUT_F32: C/add dtype
+template <int BLOCK_N, int MODE, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const GemmArgs g) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + kStages * kATileBytes;
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  // barrier layout (8 B each): full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem ptr
+  const uint32_t bar_full = bar_base;
+  const uint32_t bar_empty = bar_base + 8 * kStages;
+  const uint32_t bar_tfull = bar_base + 16 * kStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_kb = (g.K + kBlockK - 1) / kBlockK;
+  const int tiles_per_z = g.m_tiles * g.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_per_z;
+        const int rem = tile - z * tiles_per_z;
+        const int m_blk = rem / g.n_tiles;
+        const int n_blk = rem - m_blk * g.n_tiles;
+        const int z0 = z / g.Z1, z1 = z - z0 * g.Z1;
+        const int a_r = z0 * g.a_r0 + z1 * g.a_r1, a_c = z0 * g.a_c0 + z1 * g.a_c1;
+        const int b_r = z0 * g.b_r0 + z1 * g.b_r1, b_c = z0 * g.b_c0 + z1 * g.b_c1;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_arrive_expect_tx(full, Cfg::kStageBytes);
+          const uint32_t sa = smem_a + stage * kATileBytes;
+          const uint32_t sb = smem_b + stage * Cfg::kBTileBytes;
+          if (!g.a_mn) {
+            tma_load_2d(sa, &tmA, full, a_c + kb * kBlockK, a_r + m_blk * kBlockM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kBlockM / 64; ++i)
+              tma_load_2d(sa + i * (kBlockK * 128), &tmA, full, a_c + m_blk * kBlockM + i * 64,
+                          a_r + kb * kBlockK);
+          }
+          if (!g.b_mn) {
+            tma_load_2d(sb, &tmB, full, b_c + kb * kBlockK, b_r + n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i)
+              tma_load_2d(sb + i * (kBlockK * 128), &tmB, full, b_c + n_blk * BLOCK_N + i * 64,
+                          b_r + kb * kBlockK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, g.a_mn, g.b_mn);
+      // K-major: 8-row groups 1024 B apart, k-step = 32 B inside the 128 B swizzle row.
+      // MN-major: 8-k groups 1024 B apart, 64-wide M/N chunks kBlockK*128 B apart, k-step = 16 rows.
+      const uint32_t a_lbo = g.a_mn ? kBlockK * 128 : 16, b_lbo = g.b_mn ? kBlockK * 128 : 16;
+      const uint32_t a_kstep = g.a_mn ? (kUmmaK * 128) : (kUmmaK * 2);
+      const uint32_t b_kstep = g.b_mn ? (kUmmaK * 128) : (kUmmaK * 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t as_phase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * as, as_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_a + stage * kATileBytes;
+          const uint32_t sb = smem_b + stage * Cfg::kBTileBytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * as);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+      const int z = tile / tiles_per_z;
+      const int rem = tile - z * tiles_per_z;
+      const int m_blk = rem / g.n_tiles;
+      const int n_blk = rem - m_blk * g.n_tiles;
+      const int z0 = z / g.Z1, z1 = z - z0 * g.Z1;
+      const long long c_r = z0 * g.c_r0 + z1 * g.c_r1, c_c = z0 * g.c_c0 + z1 * g.c_c1;
+      const int as = it & 1;
+      const uint32_t as_phase = (it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * as, as_phase);
+      tc_fence_after();
+
+      const int m = m_blk * kBlockM + row_in_tile;
+      const bool row_ok = m < g.M;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N;
+
+      if constexpr (MODE == VQ_EPI_QKV_ROPE) {
+        // One head (64 columns) at a time; the whole head row lives in this thread's registers.
+        const int D3 = g.N / 3;  // q | k | v column blocks
+        int pos_y = 0, pos_x = 0;
+        {
+          const int p = m % g.tokens_per_frame;
+          if (p >= g.patch_start) {
+            const int idx = p - g.patch_start;
+            pos_y = idx / g.grid_w + 1;
+            pos_x = idx % g.grid_w + 1;
+          }
+        }
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 64) {
+          const int n0 = n_blk * BLOCK_N + c;
+          if (n0 >= g.N) break;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + c, r0);
+          tmem_ld32(taddr + c + 32, r1);
+          tmem_wait_ld();
+          float v[64];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = __uint_as_float(r0[i]) + __ldg(g.bias + n0 + i);
+            v[32 + i] = __uint_as_float(r1[i]) + __ldg(g.bias + n0 + 32 + i);
+          }
+          const int which = n0 / D3;  // 0 = q, 1 = k, 2 = v
+          if (which < 2 && g.apply_qknorm_rope) {
+            const float* w = which == 0 ? g.qn_w : g.kn_w;
+            const float* b = which == 0 ? g.qn_b : g.kn_b;
+            float mean = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) mean += v[i];
+            mean *= (1.0f / 64.0f);
+            float var = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+              const float d = v[i] - mean;
+              var += d * d;
+            }
+            const float rstd = rsqrtf(var * (1.0f / 64.0f) + g.qk_eps);
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+            // 2-D RoPE: dims [0,32) rotate with the row (y) position, [32,64) with the column (x).
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int pos = h == 0 ? pos_y : pos_x;
+              const float* cs = g.rope_cos + pos * 16;
+              const float* sn = g.rope_sin + pos * 16;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float co = __ldg(cs + j), si = __ldg(sn + j);
+                const float a = v[32 * h + j], b2 = v[32 * h + 16 + j];
+                v[32 * h + j] = a * co - b2 * si;
+                v[32 * h + 16 + j] = b2 * co + a * si;
+              }
+            }
+          }
+          if (which == 0) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] *= g.q_scale;
+          }
+          if (row_ok) {
+            const long long off = (c_r + m) * g.ldc + c_c + n0;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) store8<OUT_F32>(g.C, off + i, v + i);
+          }
+        }
+      } else {
+        long long out_row = c_r + m;
+        const float* pe_row = nullptr;
+        if constexpr (MODE == VQ_EPI_PATCH) {
+          const int f = m / g.n_patches;
+          const int idx = m - f * g.n_patches;
+          out_row = (long long)f * g.tokens_per_frame + g.patch_start + idx;
+          pe_row = g.pos_embed + (long long)(1 + idx) * g.N;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          const int n0 = n_blk * BLOCK_N + c;
+          if (n0 >= g.N) break;
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i8 = 0; i8 < 32; i8 += 8) {
+            const int n = n0 + i8;
+            if (n >= g.N) break;  // N is a multiple of 8
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i8 + i]) * g.alpha;
+            if (g.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + 1);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (!row_ok) continue;
+            if constexpr (MODE == VQ_EPI_GELU) {
+              if (g.aux) store8<false>(g.aux, (c_r + m) * g.ldaux + c_c + n, v);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+            }
+            if constexpr (MODE == VQ_EPI_GELU_BWD) {
+              float pre[8];
+              load8<false>(g.aux, (c_r + m) * g.ldaux + c_c + n, pre);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(pre[i]);
+            }
+            if constexpr (MODE == VQ_EPI_PATCH) {
+              const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe_row + n));
+              const float4 p1 = __ldg(reinterpret_cast<const float4*>(pe_row + n) + 1);
+              v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+              v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+            }
+            if (g.gamma) {
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(g.gamma + n));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gamma + n) + 1);
+              v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+              v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+            }
+            if (g.add) {
+              float a[8];
+              load8<OUT_F32>(g.add, (c_r + m) * g.ldadd + c_c + n, a);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += a[i];
+            }
+            store8<OUT_F32>(g.C, out_row * g.ldc + c_c + n, v);
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BLOCK_N, int MODE, bool OUT_F32>
+static int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  auto kern = gemm_kernel<BLOCK_N, MODE, OUT_F32>;
+  static bool configured = false;
+  if (!configured) {
+    VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    configured = true;
+  }
+  int grid = g.total_tiles < num_sms() ? g.total_tiles : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*tmA, *tmB, g);
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
+}
+
+static inline bool fits_i32(long long v) { return v >= INT32_MIN && v <= INT32_MAX; }
+
+}  // namespace vq
+
+extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
+  using namespace vq;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(d != nullptr, "desc is null");
+  VQ_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "M, N, K must be positive");
+  VQ_CHECK_ARG(d->N % 8 == 0, "N must be a multiple of 8");
+  VQ_CHECK_ARG(d->A && d->B && d->C, "A, B, C must be non-null");
+  VQ_CHECK_ARG(d->c_dtype == VQ_BF16 || d->c_dtype == VQ_F32, "c_dtype");
+  const int Z0 = d->Z0 > 0 ? d->Z0 : 1, Z1 = d->Z1 > 0 ? d->Z1 : 1;
+  VQ_CHECK_ARG(Z0 * Z1 == 1 || d->K % kBlockK == 0, "batched GEMM needs K % 64 == 0");
+  const int elt_c = d->c_dtype == VQ_F32 ? 4 : 2;
+  VQ_CHECK_ARG((d->ldc * elt_c) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->C) % 16) == 0,
+               "C rows must be 16-byte aligned");
+  VQ_CHECK_ARG(!d->add || ((d->ldadd * elt_c) % 16 == 0 &&
+                           (reinterpret_cast<uintptr_t>(d->add) % 16) == 0),
+               "add rows must be 16-byte aligned");
+  VQ_CHECK_ARG(!d->aux || ((d->ldaux * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->aux) % 16) == 0),
+               "aux rows must be 16-byte aligned");
+  VQ_CHECK_ARG((d->c_c0 % 8) == 0 && (d->c_c1 % 8) == 0, "C column offsets must be multiples of 8");
+  VQ_CHECK_ARG(!d->bias || (reinterpret_cast<uintptr_t>(d->bias) % 16) == 0, "bias alignment");
+  VQ_CHECK_ARG(!d->gamma || (reinterpret_cast<uintptr_t>(d->gamma) % 16) == 0, "gamma alignment");
+
+  // Tile width: 256 when the problem fills the machine with wide tiles, else 128.
+  const int m_tiles = (d->M + kBlockM - 1) / kBlockM;
+  int block_n = 256;
+  {
+    const long long tiles256 = (long long)m_tiles * ((d->N + 255) / 256) * Z0 * Z1;
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    if (d->N % 256 != 0 || tiles256 < 4LL * sms) block_n = 128;
+    if (d->epilogue == VQ_EPI_QKV_ROPE) block_n = 128;  // register budget of the per-head epilogue
+  }
+  const int n_tiles = (d->N + block_n - 1) / block_n;
+
+  // extents of the 2-D tensors the operands live in
+  const long long a_outer_need = (d->a_major ? d->K : d->M) + (long long)(Z0 - 1) * d->a_r0 +
+                                 (long long)(Z1 - 1) * d->a_r1;
+  const long long a_inner_need = (d->a_major ? d->M : d->K) + (long long)(Z0 - 1) * d->a_c0 +
+                                 (long long)(Z1 - 1) * d->a_c1;
+  const long long b_outer_need = (d->b_major ? d->K : d->N) + (long long)(Z0 - 1) * d->b_r0 +
+                                 (long long)(Z1 - 1) * d->b_r1;
+  const long long b_inner_need = (d->b_major ? d->N : d->K) + (long long)(Z0 - 1) * d->b_c0 +
+                                 (long long)(Z1 - 1) * d->b_c1;
+  const long long a_rows = d->a_rows > 0 ? d->a_rows : a_outer_need;
+  const long long a_cols = d->a_cols > 0 ? d->a_cols : a_inner_need;
+  const long long b_rows = d->b_rows > 0 ? d->b_rows : b_outer_need;
+  const long long b_cols = d->b_cols > 0 ? d->b_cols : b_inner_need;
+  VQ_CHECK_ARG(d->lda >= a_cols && d->ldb >= b_cols, "lda/ldb smaller than the row extent");
+
+  const CUtensorMap* tmA =
+      get_tmap_2d_bf16(d->A, a_cols, a_rows, d->lda, 64, d->a_major ? kBlockK : kBlockM);
+  if (!tmA) return VQ_ERR_CUDA;
+  const CUtensorMap* tmB =
+      get_tmap_2d_bf16(d->B, b_cols, b_rows, d->ldb, 64, d->b_major ? kBlockK : block_n);
+  if (!tmB) return VQ_ERR_CUDA;
+
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = d->M; g.N = d->N; g.K = d->K;
+  g.a_mn = d->a_major ? 1 : 0;
+  g.b_mn = d->b_major ? 1 : 0;
+  g.Z1 = Z1;
+  g.m_tiles = m_tiles;
+  g.n_tiles = n_tiles;
+  const long long total = (long long)m_tiles * n_tiles * Z0 * Z1;
+  VQ_CHECK_ARG(fits_i32(total), "too many tiles");
+  g.total_tiles = (int)total;
+  VQ_CHECK_ARG(fits_i32(a_rows + 512) && fits_i32(a_cols + 512) && fits_i32(b_rows + 512) &&
+                   fits_i32(b_cols + 512),
+               "operand extents exceed int32");
+  g.a_r0 = (int)d->a_r0; g.a_c0 = (int)d->a_c0; g.a_r1 = (int)d->a_r1; g.a_c1 = (int)d->a_c1;
+  g.b_r0 = (int)d->b_r0; g.b_c0 = (int)d->b_c0; g.b_r1 = (int)d->b_r1; g.b_c1 = (int)d->b_c1;
+  g.c_r0 = d->c_r0; g.c_c0 = d->c_c0; g.c_r1 = d->c_r1; g.c_c1 = d->c_c1;
+  g.C = d->C; g.ldc = d->ldc;
+  g.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+  g.bias = d->bias; g.gamma = d->gamma;
+  g.add = d->add; g.ldadd = d->ldadd;
+  g.aux = d->aux; g.ldaux = d->ldaux;
+  g.tokens_per_frame = d->tokens_per_frame; g.patch_start = d->patch_start; g.grid_w = d->grid_w;
+  g.apply_qknorm_rope = d->apply_qknorm_rope;
+  g.qn_w = d->qn_w; g.qn_b = d->qn_b; g.kn_w = d->kn_w; g.kn_b = d->kn_b;
+  g.qk_eps = d->qk_eps; g.q_scale = d->q_scale == 0.f ? 1.f : d->q_scale;
+  g.rope_cos = d->rope_cos; g.rope_sin = d->rope_sin;
+  g.n_patches = d->n_patches; g.pos_embed = d->pos_embed;
+
+  const bool f32 = d->c_dtype == VQ_F32;
+  switch (d->epilogue) {
+    case VQ_EPI_LINEAR:
+      if (block_n == 256)
+        return f32 ? launch_gemm<256, VQ_EPI_LINEAR, true>(tmA, tmB, g, stream)
+                   : launch_gemm<256, VQ_EPI_LINEAR, false>(tmA, tmB, g, stream);
+      return f32 ? launch_gemm<128, VQ_EPI_LINEAR, true>(tmA, tmB, g, stream)
+                 : launch_gemm<128, VQ_EPI_LINEAR, false>(tmA, tmB, g, stream);
+    case VQ_EPI_GELU:
+      VQ_CHECK_ARG(!f32, "GELU epilogue writes bf16");
+      VQ_CHECK_ARG(d->bias != nullptr, "GELU epilogue needs a bias");
+      return block_n == 256 ? launch_gemm<256, VQ_EPI_GELU, false>(tmA, tmB, g, stream)
+                            : launch_gemm<128, VQ_EPI_GELU, false>(tmA, tmB, g, stream);
+    case VQ_EPI_GELU_BWD:
+      VQ_CHECK_ARG(!f32, "GELU_BWD epilogue writes bf16");
+      VQ_CHECK_ARG(d->aux != nullptr, "GELU_BWD epilogue needs aux (saved pre-activation)");
+      return block_n == 256 ? launch_gemm<256, VQ_EPI_GELU_BWD, false>(tmA, tmB, g, stream)
+                            : launch_gemm<128, VQ_EPI_GELU_BWD, false>(tmA, tmB, g, stream);
+    case VQ_EPI_QKV_ROPE:
+      VQ_CHECK_ARG(!f32, "QKV epilogue writes bf16");
+      VQ_CHECK_ARG(d->bias != nullptr, "QKV epilogue needs a bias");
+      VQ_CHECK_ARG(d->N % 192 == 0, "QKV epilogue: N = 3 * heads * 64");
+      VQ_CHECK_ARG(d->tokens_per_frame > 0 && d->grid_w > 0, "QKV epilogue: token geometry");
+      VQ_CHECK_ARG(!d->apply_qknorm_rope || (d->qn_w && d->qn_b && d->kn_w && d->kn_b &&
+                                             d->rope_cos && d->rope_sin),
+                   "QKV epilogue: q/k norm and rope tables required");
+      return launch_gemm<128, VQ_EPI_QKV_ROPE, false>(tmA, tmB, g, stream);
+    case VQ_EPI_PATCH:
+      VQ_CHECK_ARG(f32, "PATCH epilogue writes the f32 token stream");
+      VQ_CHECK_ARG(d->pos_embed && d->n_patches > 0 && d->tokens_per_frame > 0, "PATCH epilogue args");
+      VQ_CHECK_ARG(Z0 * Z1 == 1, "PATCH epilogue is not batched");
+      return block_n == 256 ? launch_gemm<256, VQ_EPI_PATCH, true>(tmA, tmB, g, stream)
+                            : launch_gemm<128, VQ_EPI_PATCH, true>(tmA, tmB, g, stream);
+    default:
+      set_error("unknown epilogue");
+      return VQ_ERR_INVALID;
+  }
+}

@@ -1,0 +1,117 @@
+"""Thin torch-tensor wrappers over the C ABI (include/vq_b200.h).
+
+PyTorch is used only for device memory and streams: every function takes CUDA tensors, passes raw
+pointers to libvq_b200.so on the current stream and returns the output tensor.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import EPI_GELU, EPI_GELU_BWD, EPI_LINEAR, EPI_PATCH, EPI_QKV_ROPE, VQ_BF16, VQ_F32, GemmDesc
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (this path has no CPU implementation)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return VQ_BF16
+    if dtype == torch.float32:
+        return VQ_F32
+    raise RuntimeError(f"unsupported output dtype {dtype}")
+
+
+def gemm(
+    a: torch.Tensor,
+    b: torch.Tensor,
+    *,
+    a_major: int = 0,
+    b_major: int = 0,
+    out: Optional[torch.Tensor] = None,
+    out_dtype: torch.dtype = torch.bfloat16,
+    epilogue: int = EPI_LINEAR,
+    alpha: float = 1.0,
+    bias: Optional[torch.Tensor] = None,
+    gamma: Optional[torch.Tensor] = None,
+    add: Optional[torch.Tensor] = None,
+    aux: Optional[torch.Tensor] = None,
+    extra: Optional[dict] = None,
+) -> torch.Tensor:
+    """C = epilogue(A @ B^T) for 2-D bf16 operands.
+
+    a_major=0: a is [M,K]; a_major=1: a is [K,M] (M contiguous).  Likewise b: [N,K] or [K,N].
+    """
+    _req(a, torch.bfloat16, "a")
+    _req(b, torch.bfloat16, "b")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if a_major else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_major else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise RuntimeError(f"gemm: contraction mismatch {K} vs {Kb}")
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.a_major, d.b_major = a_major, b_major
+    d.A, d.lda = a.data_ptr(), a.stride(0)
+    d.B, d.ldb = b.data_ptr(), b.stride(0)
+    d.C, d.ldc = out.data_ptr(), out.stride(0)
+    d.c_dtype = _dtype_code(out.dtype)
+    d.Z0 = d.Z1 = 1
+    d.epilogue = epilogue
+    d.alpha = alpha
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+        d.bias = bias.data_ptr()
+    if gamma is not None:
+        _req(gamma, torch.float32, "gamma")
+        d.gamma = gamma.data_ptr()
+    if add is not None:
+        _req(add, out.dtype, "add")
+        d.add, d.ldadd = add.data_ptr(), add.stride(0)
+    if aux is not None:
+        _req(aux, torch.bfloat16, "aux")
+        d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
+    if extra:
+        for k, v in extra.items():
+            setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    _lib.check(_lib.lib().vq_gemm(C.byref(d), _stream()), "vq_gemm")
+    return out
+
+
+def gemm_desc(**kw) -> None:
+    """Launch a GEMM from explicit descriptor fields (batched / strided use)."""
+    d = GemmDesc()
+    for k, v in kw.items():
+        setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    _lib.check(_lib.lib().vq_gemm(C.byref(d), _stream()), "vq_gemm")
+
+
+def attention_fwd(qkv: torch.Tensor, n_seq: int, seq_len: int, heads: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(QK^T)V over a packed [n_seq*seq_len, 3*heads*64] bf16 buffer (q pre-scaled by log2e/8)."""
+    _req(qkv, torch.bfloat16, "qkv")
+    assert qkv.dim() == 2 and qkv.is_contiguous() and qkv.shape == (n_seq * seq_len, 3 * heads * 64)
+    if out is None:
+        out = torch.empty((n_seq * seq_len, heads * 64), device=qkv.device, dtype=torch.bfloat16)
+    _lib.check(
+        _lib.lib().vq_attention_fwd(qkv.data_ptr(), out.data_ptr(), n_seq, seq_len, heads, _stream()),
+        "vq_attention_fwd",
+    )
+    return out
