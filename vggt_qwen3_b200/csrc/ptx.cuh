@@ -52,7 +52,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if VQ_HANG_GUARD
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {  // each failed try_wait already sleeps for a HW time slice
+    if (++spins > (1u << 24)) {  // each failed try_wait already sleeps for a HW time slice
       printf("vq: mbarrier timeout block=(%d,%d,%d) thread=%d bar=0x%x parity=%u\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
       __trap();
