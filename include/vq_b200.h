@@ -120,6 +120,107 @@ int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream);
 int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32_t seq_len, int32_t heads,
                      vq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound row kernels (csrc/rowops.cu)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* K1+K2: ImageNet normalise ([UPSTREAM] aggregator.forward `(images - _resnet_mean) / _resnet_std`) fused with
+ * the im2col of the 14x14/14 patch-embed conv ([UPSTREAM] PatchEmbed.proj): images f32 [frames,3,H,W] in [0,1]
+ * -> bf16 [frames*gh*gw, Kp], column = c*patch^2 + dy*patch + dx, zero padded to Kp (multiple of 8). */
+int vq_im2col_patches(const float* images, void* out_bf16, int32_t frames, int32_t H, int32_t W, int32_t patch,
+                      int32_t Kp, vq_stream_t stream);
+
+/* K3: DINOv2 token assembly ([UPSTREAM] DinoVisionTransformer.prepare_tokens_with_masks): row 0 of every frame =
+ * cls_token + pos_embed[0]; rows 1..n_special-1 = register_tokens (no positional embedding). x is f32 [frames*P, D]. */
+int vq_init_special_tokens(float* x, const float* cls_token, const float* pos_embed0, const float* register_tokens,
+                           int32_t frames, int32_t P, int32_t D, int32_t n_special, vq_stream_t stream);
+
+/* K4: LayerNorm over the last dim (nn.LayerNorm: [UPSTREAM] Block.norm1/norm2; src/models/projector_perceiver.py:40-41).
+ * in/out dtype VQ_F32 or VQ_BF16; optional per-row mean / rstd outputs (saved for backward). D % 128 == 0. */
+int vq_layernorm(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, const float* gamma,
+                 const float* beta, int64_t rows, int32_t D, float eps, float* mean_out, float* rstd_out,
+                 vq_stream_t stream);
+
+/* K13: DINOv2 final norm on the patch rows (x_norm_patchtokens) and swap of the special rows for the aggregator's
+ * camera_token [1,2,1,D] / register_token [1,2,R,D] ([UPSTREAM] Aggregator.forward + slice_expand_and_flatten:
+ * index 0 for the first frame of each scene, 1 for the rest).  In place on the f32 stream [rows = B*S*P, D]. */
+int vq_stem_finalize(float* x, const float* gamma, const float* beta, const float* camera_token,
+                     const float* register_token, int64_t rows, int32_t D, int32_t P, int32_t S, int32_t n_special,
+                     float eps, vq_stream_t stream);
+
+/* K14+K15: out[b, t, col_off:col_off+D] = bf16(x[b*tokens_per_scene + t, :]), t < n_take.  Writes one half of
+ * `torch.cat([frame_out, global_out], -1)` restricted to the rows the caller consumes
+ * (src/models/vggt_qwen3_vlm.py:148-156 keeps `[:, :num_vis_tokens]` of the flattened last entry). */
+int vq_gather_tokens(const float* x, void* out_bf16, int32_t B, int64_t tokens_per_scene, int32_t n_take, int32_t D,
+                     int32_t out_ld, int32_t col_off, vq_stream_t stream);
+
+/* K22: training splice (src/models/vggt_qwen3_vlm.py:190-195): for every <image> position pos of sample b,
+ * inputs_embeds[b, pos:pos+n_feat] = features[b]; later positions overwrite earlier ones.  No host sync.
+ * *overflow_count (optional, device int) is incremented for every span that does not fit (the reference raises). */
+int vq_splice_overwrite(void* inputs_embeds, int32_t dtype, const int64_t* input_ids, const void* features, int32_t B,
+                        int32_t L, int32_t hidden, int32_t n_feat, int64_t image_id, int32_t* overflow_count,
+                        vq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * vq_aggregator_forward — the whole frozen VGGT Aggregator forward (csrc/aggregator.cu): replaces
+ * `self.vision_model.aggregator(images)` at src/models/vggt_qwen3_vlm.py:144 ([UPSTREAM] vggt/models/aggregator.py).
+ * All weight pointers are device pointers; the structs themselves live in host memory.
+ * Matrix weights are bf16 in nn.Linear layout [out, in]; vectors are f32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vq_block_weights {
+  const float *norm1_w, *norm1_b;
+  const void* qkv_w; /* bf16 [3D, D] */
+  const float* qkv_b;
+  const float *q_norm_w, *q_norm_b, *k_norm_w, *k_norm_b; /* [64]; all NULL for the DINOv2 stem blocks */
+  const void* proj_w; /* bf16 [D, D] */
+  const float* proj_b;
+  const float* ls1; /* LayerScale gamma [D] */
+  const float *norm2_w, *norm2_b;
+  const void* fc1_w; /* bf16 [hidden, D] */
+  const float* fc1_b;
+  const void* fc2_w; /* bf16 [D, hidden] */
+  const float* fc2_b;
+  const float* ls2;
+} vq_block_weights;
+
+typedef struct vq_aggregator_weights {
+  const void* patch_w; /* bf16 [D, Kp]: conv weight flattened (c, dy, dx), zero padded to Kp */
+  const float* patch_b;
+  const float* cls_token;       /* [D] */
+  const float* pos_embed;       /* [1 + gh*gw, D], already interpolated to the patch grid */
+  const float* register_tokens; /* DINOv2 registers [R, D] */
+  const vq_block_weights* stem_blocks;
+  int32_t n_stem;
+  const float *stem_norm_w, *stem_norm_b;
+  const float* camera_token;   /* [2, 1, D] */
+  const float* register_token; /* [2, R, D] */
+  const vq_block_weights* frame_blocks;
+  const vq_block_weights* global_blocks;
+  int32_t depth;
+  const float *rope_cos, *rope_sin; /* [rope_max_pos + 1, 16] */
+  int32_t rope_max_pos;
+} vq_aggregator_weights;
+
+typedef struct vq_aggregator_cfg {
+  int32_t B, S;        /* scenes, frames per scene */
+  int32_t H, W, patch; /* 518, 518, 14 */
+  int32_t D, heads, hidden; /* 1024, 16 (head_dim must be 64), 4096 */
+  int32_t n_special;   /* patch_start_idx = 1 + registers = 5 */
+  int32_t Kp;          /* padded im2col width (592) */
+  float stem_eps, block_eps, qk_eps; /* 1e-6, 1e-5, 1e-5 */
+} vq_aggregator_cfg;
+
+size_t vq_aggregator_workspace_bytes(const vq_aggregator_cfg* cfg);
+
+/* images: f32 [B,S,3,H,W] in [0,1].
+ * out_tokens: bf16 [B, n_take, 2D] = cat(frame_out, global_out)[-1] flattened over views, first n_take tokens
+ *             (n_take = num_vis_tokens for encode_images; S*P for the full last list entry).
+ * out_all: NULL, or `depth` device pointers, each bf16 [B, S*P, 2D], receiving every iteration's concat
+ *          (the full list the upstream call returns; the reference only reads [-1]). */
+int vq_aggregator_forward(const vq_aggregator_cfg* cfg, const vq_aggregator_weights* w, const float* images,
+                          void* out_tokens, int32_t n_take, void* const* out_all, void* workspace,
+                          size_t workspace_bytes, vq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

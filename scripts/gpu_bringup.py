@@ -68,8 +68,8 @@ def case_gemm(M, N, K, a_major=0, b_major=0, epi="linear", out_f32=False, timing
         cdf = 0.5 * (1 + torch.erf(x / math.sqrt(2)))
         pdf = torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
         ref = ref * (cdf + x * pdf)
-    out = ops.gemm(a_in, b_in, a_major=a_major, b_major=b_major,
-                   out_dtype=torch.float32 if out_f32 else torch.bfloat16, **kw)
+    kw["out_dtype"] = torch.float32 if out_f32 else torch.bfloat16
+    out = ops.gemm(a_in, b_in, a_major=a_major, b_major=b_major, **kw)
     torch.cuda.synchronize()
     rel = _rel(out, ref)
     msg = f"rel={rel:.3e} cos={_cos(out, ref):.6f}"

@@ -1,0 +1,48 @@
+"""GPU parity: CUDA aggregator (through the C ABI) vs the fp32 oracle restatement on the same seeded inputs."""
+import pytest
+import torch
+
+from oracle.aggregator_ref import AggregatorConfig, aggregator_forward, init_aggregator_state
+from tests.parity import assert_token_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(cfg: AggregatorConfig, state):
+    from vggt_qwen3_b200.aggregator import Aggregator
+
+    agg = Aggregator(img_size=cfg.img_size, patch_size=cfg.patch_size, embed_dim=cfg.embed_dim, depth=cfg.depth,
+                     num_heads=cfg.num_heads, num_register_tokens=cfg.num_register_tokens, stem_depth=cfg.stem_depth)
+    missing = agg.load_state_dict(state, strict=True)  # upstream key layout must match exactly
+    return agg.cuda().eval()
+
+
+CASES = [
+    # (img, D, heads, depth, stem_depth, B, S, sensitised)
+    (56, 128, 2, 2, 2, 2, 3, False),
+    (56, 128, 2, 2, 2, 2, 3, True),
+    (126, 256, 4, 3, 2, 1, 2, True),
+    (154, 128, 2, 2, 1, 3, 1, True),   # 11x11 patches: P = 126, ragged vs every tile size
+]
+
+
+@pytest.mark.parametrize("img,D,heads,depth,stem_depth,B,S,sens", CASES)
+def test_aggregator_matches_oracle(img, D, heads, depth, stem_depth, B, S, sens):
+    cfg = AggregatorConfig(img_size=img, embed_dim=D, num_heads=heads, depth=depth, stem_depth=stem_depth)
+    state = init_aggregator_state(cfg, seed=0, sensitised=sens)
+    images = torch.rand(B, S, 3, img, img, generator=torch.Generator().manual_seed(1))
+    ref_list, ref_idx = aggregator_forward(state, images, cfg, return_all=True)
+    agg = _build(cfg, state)
+    out_list, idx = agg(images.cuda(), return_all=True)
+    assert idx == ref_idx == 5
+    assert len(out_list) == len(ref_list) == depth
+    for i, (o, r) in enumerate(zip(out_list, ref_list)):
+        assert o.dtype == torch.bfloat16
+        assert_token_parity(o, r, f"iteration {i}")
+    # default call: only the last entry, same values
+    last_only, _ = agg(images.cuda())
+    assert len(last_only) == 1 and torch.equal(last_only[-1], out_list[-1])
+    # encode path: first n tokens of the view-flattened last entry
+    n = 17
+    taken = agg.encode_tokens(images.cuda(), n)
+    assert torch.equal(taken, out_list[-1].reshape(B, -1, 2 * D)[:, :n])

@@ -47,6 +47,41 @@ class GemmDesc(C.Structure):
     ]
 
 
+class BlockWeights(C.Structure):
+    """Mirror of `vq_block_weights`."""
+
+    _fields_ = [(n, C.c_void_p) for n in (
+        "norm1_w", "norm1_b", "qkv_w", "qkv_b", "q_norm_w", "q_norm_b", "k_norm_w", "k_norm_b",
+        "proj_w", "proj_b", "ls1", "norm2_w", "norm2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")]
+
+
+class AggregatorWeights(C.Structure):
+    """Mirror of `vq_aggregator_weights`."""
+
+    _fields_ = [
+        ("patch_w", C.c_void_p), ("patch_b", C.c_void_p),
+        ("cls_token", C.c_void_p), ("pos_embed", C.c_void_p), ("register_tokens", C.c_void_p),
+        ("stem_blocks", C.POINTER(BlockWeights)), ("n_stem", C.c_int32),
+        ("stem_norm_w", C.c_void_p), ("stem_norm_b", C.c_void_p),
+        ("camera_token", C.c_void_p), ("register_token", C.c_void_p),
+        ("frame_blocks", C.POINTER(BlockWeights)), ("global_blocks", C.POINTER(BlockWeights)),
+        ("depth", C.c_int32),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_max_pos", C.c_int32),
+    ]
+
+
+class AggregatorCfg(C.Structure):
+    """Mirror of `vq_aggregator_cfg`."""
+
+    _fields_ = [
+        ("B", C.c_int32), ("S", C.c_int32),
+        ("H", C.c_int32), ("W", C.c_int32), ("patch", C.c_int32),
+        ("D", C.c_int32), ("heads", C.c_int32), ("hidden", C.c_int32),
+        ("n_special", C.c_int32), ("Kp", C.c_int32),
+        ("stem_eps", C.c_float), ("block_eps", C.c_float), ("qk_eps", C.c_float),
+    ]
+
+
 _lib = None
 
 
@@ -59,6 +94,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vq_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.vq_attention_fwd.restype = C.c_int
     lib.vq_attention_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.vq_aggregator_workspace_bytes.restype = C.c_size_t
+    lib.vq_aggregator_workspace_bytes.argtypes = [C.POINTER(AggregatorCfg)]
     for name, argtypes in _EXTRA_DECLS.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int
@@ -67,7 +104,16 @@ def _declare(lib: C.CDLL) -> None:
 
 # name -> argtypes for the row/elementwise entry points (all return int status)
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
-_EXTRA_DECLS: dict[str, list] = {}
+_EXTRA_DECLS: dict[str, list] = {
+    "vq_im2col_patches": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "vq_init_special_tokens": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "vq_layernorm": [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp],
+    "vq_stem_finalize": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
+    "vq_gather_tokens": [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp],
+    "vq_splice_overwrite": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp],
+    "vq_aggregator_forward": [C.POINTER(AggregatorCfg), C.POINTER(AggregatorWeights), _vp, _vp, _i32,
+                              C.POINTER(C.c_void_p), _vp, C.c_size_t, _vp],
+}
 
 
 def lib() -> C.CDLL:

@@ -1,0 +1,358 @@
+// HBM-bound row kernels of the aggregator path: normalise+im2col, token assembly, LayerNorm,
+// DINOv2 final-norm + special-token swap, last-layer token gather, inputs_embeds splice.
+// All use 128-bit (or widest aligned) accesses, one warp per row with shuffle reductions.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vq {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2 front: (x - mean) / std, then im2col of 14x14/14 patches into bf16 rows [c*ps*ps + dy*ps + dx].
+// One CTA per (frame, patch row): the 3 x ps x W strip is read coalesced, staged in smem as bf16,
+// and written out one patch row (Kp bf16) at a time.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W, int ps,
+              int gh, int gw, int Kp) {
+  extern __shared__ __nv_bfloat16 strip[];  // [3][ps][Wc], Wc = gw*ps
+  const int f = blockIdx.x / gh, gy = blockIdx.x % gh;
+  const int Wc = gw * ps;
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float istd[3] = {1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f};
+  const int n = 3 * ps * Wc;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = i % Wc;
+    const int dy = (i / Wc) % ps;
+    const int c = i / (Wc * ps);
+    const float v = img[(((long long)f * 3 + c) * H + gy * ps + dy) * W + x];
+    strip[i] = __float2bfloat16((v - mean[c]) * istd[c]);
+  }
+  __syncthreads();
+  const int K = 3 * ps * ps;
+  const int total = gw * Kp;
+  __nv_bfloat16* dst = out + ((long long)f * gh + gy) * gw * Kp;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int gx = i / Kp, k = i - gx * Kp;
+    __nv_bfloat16 v = __float2bfloat16(0.f);
+    if (k < K) {
+      const int c = k / (ps * ps);
+      const int r = k - c * ps * ps;
+      const int dy = r / ps, dx = r - dy * ps;
+      v = strip[(c * ps + dy) * Wc + gx * ps + dx];
+    }
+    dst[i] = v;
+  }
+}
+
+// K3: rows 0..n_special-1 of every frame: cls + pos_embed[0], then the register tokens (f32 stream).
+__global__ void init_special_kernel(float* __restrict__ x, const float* __restrict__ cls,
+                                    const float* __restrict__ pos0, const float* __restrict__ regs,
+                                    int P, int D, int n_special) {
+  const int f = blockIdx.x;
+  for (int i = threadIdx.x; i < n_special * D; i += blockDim.x) {
+    const int r = i / D, c = i - r * D;
+    const float v = r == 0 ? cls[c] + pos0[c] : regs[(r - 1) * D + c];
+    x[((long long)f * P + r) * D + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dimension, one warp per row, row held in registers (two-pass variance).
+// IN_F32 / OUT_F32 select the stream dtypes; VEC = D / 128 (each lane owns VEC float4 groups).
+// ------------------------------------------------------------------------------------------------
+template <int VEC, bool IN_F32>
+__device__ __forceinline__ void load_row(const void* in, long long row, int D, int lane, float (&v)[VEC][4]) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    if constexpr (IN_F32) {
+      const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + row * D + col);
+      v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(in) + row * D + col);
+      v[i][0] = bf16_lo(t.x); v[i][1] = bf16_hi(t.x); v[i][2] = bf16_lo(t.y); v[i][3] = bf16_hi(t.y);
+    }
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void row_stats(const float (&v)[VEC][4], int D, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+  mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = v[i][j] - mean;
+      q += d * d;
+    }
+  }
+  rstd = rsqrtf(warp_sum(q) / D + eps);
+}
+template <int VEC, bool OUT_F32>
+__device__ __forceinline__ void norm_store_row(void* out, long long row, int D, int lane, const float (&v)[VEC][4],
+                                               float mean, float rstd, const float* gamma, const float* beta) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float y0 = (v[i][0] - mean) * rstd * g.x + b.x;
+    const float y1 = (v[i][1] - mean) * rstd * g.y + b.y;
+    const float y2 = (v[i][2] - mean) * rstd * g.z + b.z;
+    const float y3 = (v[i][3] - mean) * rstd * g.w + b.w;
+    if constexpr (OUT_F32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * D + col) = make_float4(y0, y1, y2, y3);
+    } else {
+      uint2 u;
+      u.x = pack_bf16x2(y0, y1);
+      u.y = pack_bf16x2(y2, y3);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * D + col) = u;
+    }
+  }
+}
+
+template <int VEC, bool IN_F32, bool OUT_F32>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ in, void* __restrict__ out, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, long long rows, int D, float eps,
+                 float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[VEC][4];
+  load_row<VEC, IN_F32>(in, row, D, lane, v);
+  float mean, rstd;
+  row_stats<VEC>(v, D, eps, mean, rstd);
+  norm_store_row<VEC, OUT_F32>(out, row, D, lane, v, mean, rstd, gamma, beta);
+  if (mean_out && lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// K13: DINOv2 final LayerNorm on the patch rows (in place, f32) + camera/register tokens swapped into
+// the special rows (token index 0 for the first frame of a scene, 1 for the others).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+stem_finalize_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ camera, const float* __restrict__ regs, long long rows, int D,
+                     int P, int S, int n_special, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long frame = row / P;
+  const int p = (int)(row - frame * P);
+  if (p < n_special) {
+    const int which = (frame % S) == 0 ? 0 : 1;
+    // camera_token [1,2,1,D], register_token [1,2,R,D]
+    const float* src = p == 0 ? camera + (long long)which * D
+                              : regs + ((long long)which * (n_special - 1) + (p - 1)) * D;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(x + row * D + col) = __ldg(reinterpret_cast<const float4*>(src + col));
+    }
+    return;
+  }
+  float v[VEC][4];
+  load_row<VEC, true>(x, row, D, lane, v);
+  float mean, rstd;
+  row_stats<VEC>(v, D, eps, mean, rstd);
+  norm_store_row<VEC, true>(x, row, D, lane, v, mean, rstd, gamma, beta);
+}
+
+// K14 + K15: out[b, t, col_off : col_off + D] = bf16(x[b * tokens_per_scene + t, :]) for t < n_take.
+__global__ void __launch_bounds__(256)
+gather_tokens_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int D, long long tokens_per_scene,
+                     int n_take, int out_ld, int col_off, long long total_rows) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= total_rows) return;
+  const long long b = r / n_take;
+  const int t = (int)(r - b * n_take);
+  const float* src = x + (b * tokens_per_scene + t) * D;
+  __nv_bfloat16* dst = out + r * out_ld + col_off;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(src + c);
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + c) = u;
+  }
+}
+
+// K22: training splice.  For every row r of sample b the last <image> position pos <= r with r - pos < n
+// wins (the reference loops over positions in ascending order, later spans overwrite earlier ones).
+// One warp per (b, r); no host synchronisation.  ELT = bytes per element of embeds/features.
+template <typename T>
+__global__ void __launch_bounds__(256)
+splice_overwrite_kernel(T* __restrict__ embeds, const long long* __restrict__ ids, const T* __restrict__ feats,
+                        int B, int L, int Hd, int n, long long image_id, int* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)B * L) return;
+  const int b = (int)(w / L), r = (int)(w - (long long)b * L);
+  const long long* row_ids = ids + (long long)b * L;
+  int best = -1;
+  for (int p = r - lane; p > r - n && p >= 0; p -= 32)
+    if (row_ids[p] == image_id) { best = p; break; }  // first hit per lane is that lane's largest
+  best = warp_max_i(best);
+  if (overflow && lane == 0 && row_ids[r] == image_id && r + n > L) atomicAdd(overflow, 1);
+  if (best < 0) return;
+  const T* src = feats + ((long long)b * n + (r - best)) * Hd;
+  T* dst = embeds + ((long long)b * L + r) * Hd;
+  constexpr int kVec = 16 / sizeof(T);
+  for (int c = lane * kVec; c < Hd; c += 32 * kVec)
+    *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(src + c);
+}
+
+}  // namespace vq
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+using namespace vq;
+
+extern "C" int vq_im2col_patches(const float* images, void* out_bf16, int32_t frames, int32_t H, int32_t W,
+                                 int32_t patch, int32_t Kp, vq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(images && out_bf16, "null pointer");
+  VQ_CHECK_ARG(frames > 0 && patch > 0 && H >= patch && W >= patch, "image geometry");
+  const int gh = H / patch, gw = W / patch;
+  VQ_CHECK_ARG(Kp >= 3 * patch * patch && Kp % 8 == 0, "Kp must be >= 3*patch^2 and a multiple of 8");
+  const size_t smem = (size_t)3 * patch * gw * patch * sizeof(__nv_bfloat16);
+  VQ_CHECK_ARG(smem <= 200 * 1024, "image too wide for the im2col strip");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    VQ_CHECK_CUDA(cudaFuncSetAttribute(im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  im2col_kernel<<<frames * gh, 256, smem, stream>>>(images, reinterpret_cast<__nv_bfloat16*>(out_bf16), H, W, patch,
+                                                    gh, gw, Kp);
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
+}
+
+extern "C" int vq_init_special_tokens(float* x, const float* cls_token, const float* pos_embed0,
+                                      const float* register_tokens, int32_t frames, int32_t P, int32_t D,
+                                      int32_t n_special, vq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(x && cls_token && pos_embed0 && register_tokens, "null pointer");
+  VQ_CHECK_ARG(frames > 0 && P >= n_special && n_special >= 1, "token geometry");
+  init_special_kernel<<<frames, 256, 0, stream>>>(x, cls_token, pos_embed0, register_tokens, P, D, n_special);
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
+}
+
+template <bool IN_F32, bool OUT_F32>
+static int launch_ln(const void* in, void* out, const float* gamma, const float* beta, long long rows, int D,
+                     float eps, float* mean_out, float* rstd_out, cudaStream_t stream) {
+  const int warps = 8;
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+#define VQ_LN_CASE(V)                                                                                      \
+  case V:                                                                                                  \
+    layernorm_kernel<V, IN_F32, OUT_F32><<<grid, warps * 32, 0, stream>>>(in, out, gamma, beta, rows, D, eps, \
+                                                                          mean_out, rstd_out);             \
+    break;
+  switch (D / 128) {
+    VQ_LN_CASE(1) VQ_LN_CASE(2) VQ_LN_CASE(3) VQ_LN_CASE(4) VQ_LN_CASE(6) VQ_LN_CASE(8) VQ_LN_CASE(16)
+    VQ_LN_CASE(32)
+    default:
+      set_error("layernorm: unsupported width (D/128 must be one of 1,2,3,4,6,8,16,32)");
+      return VQ_ERR_UNSUPPORTED;
+  }
+#undef VQ_LN_CASE
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
+}
+
+extern "C" int vq_layernorm(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, const float* gamma,
+                            const float* beta, int64_t rows, int32_t D, float eps, float* mean_out,
+                            float* rstd_out, vq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(in && out && gamma && beta, "null pointer");
+  VQ_CHECK_ARG(rows > 0 && D > 0 && D % 128 == 0, "rows > 0 and D % 128 == 0 required");
+  VQ_CHECK_ARG((mean_out == nullptr) == (rstd_out == nullptr), "mean_out and rstd_out go together");
+  const bool i32 = in_dtype == VQ_F32, o32 = out_dtype == VQ_F32;
+  if (i32 && !o32) return launch_ln<true, false>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
+  if (i32 && o32) return launch_ln<true, true>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
+  if (!i32 && !o32) return launch_ln<false, false>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
+  return launch_ln<false, true>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
+}
+
+extern "C" int vq_stem_finalize(float* x, const float* gamma, const float* beta, const float* camera_token,
+                                const float* register_token, int64_t rows, int32_t D, int32_t P, int32_t S,
+                                int32_t n_special, float eps, vq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(x && gamma && beta && camera_token && register_token, "null pointer");
+  VQ_CHECK_ARG(rows > 0 && D % 128 == 0 && P > n_special && S > 0, "geometry");
+  const int warps = 8;
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+#define VQ_SF_CASE(V)                                                                                       \
+  case V:                                                                                                   \
+    stem_finalize_kernel<V><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, camera_token, register_token, rows, \
+                                                             D, P, S, n_special, eps);                      \
+    break;
+  switch (D / 128) {
+    VQ_SF_CASE(1) VQ_SF_CASE(2) VQ_SF_CASE(3) VQ_SF_CASE(4) VQ_SF_CASE(6) VQ_SF_CASE(8)
+    default:
+      set_error("stem_finalize: unsupported width");
+      return VQ_ERR_UNSUPPORTED;
+  }
+#undef VQ_SF_CASE
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
+}
+
+extern "C" int vq_gather_tokens(const float* x, void* out_bf16, int32_t B, int64_t tokens_per_scene, int32_t n_take,
+                                int32_t D, int32_t out_ld, int32_t col_off, vq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(x && out_bf16, "null pointer");
+  VQ_CHECK_ARG(B > 0 && n_take > 0 && n_take <= tokens_per_scene && D % 4 == 0, "geometry");
+  VQ_CHECK_ARG(out_ld % 4 == 0 && col_off % 4 == 0 && col_off + D <= out_ld, "output layout");
+  const long long total = (long long)B * n_take;
+  const int warps = 8;
+  gather_tokens_kernel<<<(unsigned)((total + warps - 1) / warps), warps * 32, 0, stream>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out_bf16), D, tokens_per_scene, n_take, out_ld, col_off, total);
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
+}
+
+extern "C" int vq_splice_overwrite(void* inputs_embeds, int32_t dtype, const int64_t* input_ids, const void* features,
+                                   int32_t B, int32_t L, int32_t hidden, int32_t n_feat, int64_t image_id,
+                                   int32_t* overflow_count, vq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(inputs_embeds && input_ids && features, "null pointer");
+  VQ_CHECK_ARG(B > 0 && L > 0 && n_feat > 0, "geometry");
+  const int elt = dtype == VQ_F32 ? 4 : 2;
+  VQ_CHECK_ARG((hidden * elt) % 16 == 0, "hidden size must give 16-byte rows");
+  VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(inputs_embeds) % 16) == 0 && (reinterpret_cast<uintptr_t>(features) % 16) == 0,
+               "16-byte alignment");
+  const long long total = (long long)B * L;
+  const int warps = 8;
+  const unsigned grid = (unsigned)((total + warps - 1) / warps);
+  if (dtype == VQ_F32)
+    splice_overwrite_kernel<float><<<grid, warps * 32, 0, stream>>>(
+        reinterpret_cast<float*>(inputs_embeds), reinterpret_cast<const long long*>(input_ids),
+        reinterpret_cast<const float*>(features), B, L, hidden, n_feat, image_id, overflow_count);
+  else
+    splice_overwrite_kernel<__nv_bfloat16><<<grid, warps * 32, 0, stream>>>(
+        reinterpret_cast<__nv_bfloat16*>(inputs_embeds), reinterpret_cast<const long long*>(input_ids),
+        reinterpret_cast<const __nv_bfloat16*>(features), B, L, hidden, n_feat, image_id, overflow_count);
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
+}
