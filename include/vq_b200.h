@@ -221,6 +221,103 @@ int vq_aggregator_forward(const vq_aggregator_cfg* cfg, const vq_aggregator_weig
                           void* out_tokens, int32_t n_take, void* const* out_all, void* workspace,
                           size_t workspace_bytes, vq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Perceiver projector row kernels (csrc/perceiver_ops.cu)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* softmax over the first T columns of each f32 score row -> bf16 probabilities [rows, Tp] (columns T..Tp-1 = 0).
+ * The attention core of nn.MultiheadAttention (src/models/projector_perceiver.py:33,45). T, Tp <= 1024. */
+int vq_softmax_fwd(const float* scores, void* probs_bf16, int64_t rows, int32_t T, int32_t ld_scores, int32_t Tp,
+                   vq_stream_t stream);
+/* dS = scale * P .* (dP - rowsum(dP .* P)) -> bf16 [rows, Tp] */
+int vq_softmax_bwd(const void* probs_bf16, const float* dprobs, void* dscores_bf16, int64_t rows, int32_t T,
+                   int32_t ld_dprobs, int32_t Tp, float scale, vq_stream_t stream);
+/* LayerNorm backward (autograd of nn.LayerNorm at src/models/projector_perceiver.py:47,49): dz (bf16) from dy, the
+ * saved LN input z and its row statistics; dgamma/dbeta (f32 [D]) are ACCUMULATED (+=). */
+int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const float* mean, const float* rstd,
+                     const float* gamma, void* dz_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t D,
+                     vq_stream_t stream);
+/* out[n] += sum_m x[m, n]  (bias gradients) */
+int vq_colsum(const void* x, int32_t dtype, float* out, int64_t rows, int32_t N, int64_t ld, vq_stream_t stream);
+/* f32 master -> bf16 compute copy */
+int vq_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, vq_stream_t stream);
+/* out[b, :] = src[:]  — `self.latents.unsqueeze(0).expand(B, -1, -1)` (src/models/projector_perceiver.py:79) */
+int vq_broadcast_rows(const void* src_bf16, void* out_bf16, int64_t n, int32_t B, vq_stream_t stream);
+/* out[i] (+)= sum_b in[b, i] — gradient of the expanded latents */
+int vq_reduce_batch(const void* in_bf16, float* out, int64_t n, int32_t B, int32_t accumulate, vq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * vq_perceiver_forward / vq_perceiver_backward (csrc/perceiver.cu): PerceiverProjector.forward
+ * (src/models/projector_perceiver.py:70-82, layer :44-50) and its autograd backward.
+ * bf16 compute copies of the f32 master weights are passed in (DeepSpeed-bf16 policy of the reference,
+ * configs/deepspeed_zero3.json:4-6); gradients are produced in f32 directly from the TMEM accumulators.
+ * Dropout sites (:33,37,42,46,49) are identity here (eval / p = 0).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vq_perceiver_cfg {
+  int32_t B, T;       /* samples, context tokens per sample (T % 8 == 0, T <= 1024) */
+  int32_t in_dim;     /* 2048 */
+  int32_t E, heads;   /* latent_dim 4096, num_heads 8  (E/heads % 64 == 0) */
+  int32_t Lq;         /* num_latents 128 */
+  int32_t layers;     /* 6 */
+  int32_t ffn;        /* 16384 */
+  int32_t out_dim;    /* text hidden size, 2560 */
+  float ln_eps;       /* 1e-5 */
+  int32_t out_dtype;  /* VQ_BF16 or VQ_F32 */
+} vq_perceiver_cfg;
+
+typedef struct vq_perceiver_layer_weights {
+  const void* in_proj_w; /* bf16 [3E, E]  (nn.MultiheadAttention.in_proj_weight: q | k | v row blocks) */
+  const float* in_proj_b; /* [3E] */
+  const void* out_proj_w; /* bf16 [E, E] */
+  const float* out_proj_b;
+  const float *norm1_w, *norm1_b;
+  const void* fc1_w; /* bf16 [ffn, E]  (mlp.0) */
+  const float* fc1_b;
+  const void* fc2_w; /* bf16 [E, ffn]  (mlp.3) */
+  const float* fc2_b;
+  const float *norm2_w, *norm2_b;
+} vq_perceiver_layer_weights;
+
+typedef struct vq_perceiver_weights {
+  const void* latents;   /* bf16 [Lq, E] */
+  const void* in_proj_w; /* bf16 [E, in_dim] */
+  const float* in_proj_b;
+  const vq_perceiver_layer_weights* layers;
+  const void* out_proj_w; /* bf16 [out_dim, E] */
+  const float* out_proj_b;
+} vq_perceiver_weights;
+
+/* f32 gradient destinations, same shapes as the parameters.  Every buffer is OVERWRITTEN unless accumulate != 0. */
+typedef struct vq_perceiver_layer_grads {
+  float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b, *norm1_w, *norm1_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b,
+      *norm2_w, *norm2_b;
+} vq_perceiver_layer_grads;
+
+typedef struct vq_perceiver_grads {
+  float* latents;
+  float *in_proj_w, *in_proj_b;
+  const vq_perceiver_layer_grads* layers;
+  float *out_proj_w, *out_proj_b;
+  int32_t accumulate;
+} vq_perceiver_grads;
+
+/* Called on the host right after the work producing the gradients of `layer` has been ENQUEUED
+ * (layer = cfg.layers for out_proj, cfg.layers-1 .. 0 for the Perceiver layers, -1 for in_proj + latents),
+ * so the caller can record an event and start that bucket's NCCL all-reduce on another stream. */
+typedef void (*vq_layer_done_fn)(int32_t layer, void* user);
+
+size_t vq_perceiver_saved_bytes(const vq_perceiver_cfg* cfg);     /* activations kept for backward */
+size_t vq_perceiver_workspace_bytes(const vq_perceiver_cfg* cfg); /* scratch for either direction */
+
+/* tokens: bf16 [B*T, in_dim]; out: [B*Lq, out_dim] in cfg.out_dtype; saved: vq_perceiver_saved_bytes (1024-aligned). */
+int vq_perceiver_forward(const vq_perceiver_cfg* cfg, const vq_perceiver_weights* w, const void* tokens_bf16,
+                         void* out, void* saved, void* workspace, vq_stream_t stream);
+/* grad_out: bf16 [B*Lq, out_dim]; grad_tokens: f32 [B*T, in_dim] or NULL. */
+int vq_perceiver_backward(const vq_perceiver_cfg* cfg, const vq_perceiver_weights* w, const void* tokens_bf16,
+                          const void* grad_out_bf16, const void* saved, const vq_perceiver_grads* grads,
+                          float* grad_tokens, void* workspace, vq_layer_done_fn on_layer_done, void* user,
+                          vq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,55 @@ class AggregatorCfg(C.Structure):
     ]
 
 
+class PerceiverCfg(C.Structure):
+    """Mirror of `vq_perceiver_cfg`."""
+
+    _fields_ = [
+        ("B", C.c_int32), ("T", C.c_int32), ("in_dim", C.c_int32), ("E", C.c_int32), ("heads", C.c_int32),
+        ("Lq", C.c_int32), ("layers", C.c_int32), ("ffn", C.c_int32), ("out_dim", C.c_int32),
+        ("ln_eps", C.c_float), ("out_dtype", C.c_int32),
+    ]
+
+
+_PLAYER_FIELDS = ("in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "norm1_w", "norm1_b",
+                  "fc1_w", "fc1_b", "fc2_w", "fc2_b", "norm2_w", "norm2_b")
+
+
+class PerceiverLayerWeights(C.Structure):
+    """Mirror of `vq_perceiver_layer_weights`."""
+
+    _fields_ = [(n, C.c_void_p) for n in _PLAYER_FIELDS]
+
+
+class PerceiverWeights(C.Structure):
+    """Mirror of `vq_perceiver_weights`."""
+
+    _fields_ = [
+        ("latents", C.c_void_p), ("in_proj_w", C.c_void_p), ("in_proj_b", C.c_void_p),
+        ("layers", C.POINTER(PerceiverLayerWeights)),
+        ("out_proj_w", C.c_void_p), ("out_proj_b", C.c_void_p),
+    ]
+
+
+class PerceiverLayerGrads(C.Structure):
+    """Mirror of `vq_perceiver_layer_grads` (same field order as the weights)."""
+
+    _fields_ = [(n, C.c_void_p) for n in _PLAYER_FIELDS]
+
+
+class PerceiverGrads(C.Structure):
+    """Mirror of `vq_perceiver_grads`."""
+
+    _fields_ = [
+        ("latents", C.c_void_p), ("in_proj_w", C.c_void_p), ("in_proj_b", C.c_void_p),
+        ("layers", C.POINTER(PerceiverLayerGrads)),
+        ("out_proj_w", C.c_void_p), ("out_proj_b", C.c_void_p),
+        ("accumulate", C.c_int32),
+    ]
+
+
+LayerDoneFn = C.CFUNCTYPE(None, C.c_int32, C.c_void_p)
+
 _lib = None
 
 
@@ -96,6 +145,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.vq_attention_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.vq_aggregator_workspace_bytes.restype = C.c_size_t
     lib.vq_aggregator_workspace_bytes.argtypes = [C.POINTER(AggregatorCfg)]
+    for name in ("vq_perceiver_saved_bytes", "vq_perceiver_workspace_bytes"):
+        getattr(lib, name).restype = C.c_size_t
+        getattr(lib, name).argtypes = [C.POINTER(PerceiverCfg)]
     for name, argtypes in _EXTRA_DECLS.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int
@@ -111,6 +163,16 @@ _EXTRA_DECLS: dict[str, list] = {
     "vq_stem_finalize": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
     "vq_gather_tokens": [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp],
     "vq_splice_overwrite": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp],
+    "vq_softmax_fwd": [_vp, _vp, _i64, _i32, _i32, _i32, _vp],
+    "vq_softmax_bwd": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp],
+    "vq_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "vq_colsum": [_vp, _i32, _vp, _i64, _i32, _i64, _vp],
+    "vq_cast_f32_bf16": [_vp, _vp, _i64, _vp],
+    "vq_broadcast_rows": [_vp, _vp, _i64, _i32, _vp],
+    "vq_reduce_batch": [_vp, _vp, _i64, _i32, _i32, _vp],
+    "vq_perceiver_forward": [C.POINTER(PerceiverCfg), C.POINTER(PerceiverWeights), _vp, _vp, _vp, _vp, _vp],
+    "vq_perceiver_backward": [C.POINTER(PerceiverCfg), C.POINTER(PerceiverWeights), _vp, _vp, _vp,
+                              C.POINTER(PerceiverGrads), _vp, _vp, LayerDoneFn, _vp, _vp],
     "vq_aggregator_forward": [C.POINTER(AggregatorCfg), C.POINTER(AggregatorWeights), _vp, _vp, _i32,
                               C.POINTER(C.c_void_p), _vp, C.c_size_t, _vp],
 }

@@ -115,3 +115,57 @@ def attention_fwd(qkv: torch.Tensor, n_seq: int, seq_len: int, heads: int,
         "vq_attention_fwd",
     )
     return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out_dtype: torch.dtype = torch.bfloat16, return_stats: bool = False):
+    """Row LayerNorm of a 2-D f32/bf16 tensor (D % 128 == 0)."""
+    assert x.dim() == 2 and x.is_contiguous() and x.is_cuda
+    rows, D = x.shape
+    out = torch.empty(rows, D, device=x.device, dtype=out_dtype)
+    mean = rstd = None
+    if return_stats:
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _req(gamma, torch.float32, "gamma")
+    _req(beta, torch.float32, "beta")
+    _lib.check(
+        _lib.lib().vq_layernorm(x.data_ptr(), _dtype_code(x.dtype), out.data_ptr(), _dtype_code(out_dtype),
+                                gamma.data_ptr(), beta.data_ptr(), rows, D, eps, _ptr(mean), _ptr(rstd), _stream()),
+        "vq_layernorm")
+    return (out, mean, rstd) if return_stats else out
+
+
+def layernorm_bwd(dy: torch.Tensor, z: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor):
+    """Returns (dz bf16, dgamma f32, dbeta f32) for bf16 dy and saved LN input z."""
+    _req(dy, torch.bfloat16, "dy")
+    _req(z, torch.bfloat16, "z")
+    rows, D = z.shape
+    dz = torch.empty_like(z)
+    dgamma = torch.zeros(D, device=z.device, dtype=torch.float32)
+    dbeta = torch.zeros(D, device=z.device, dtype=torch.float32)
+    _lib.check(
+        _lib.lib().vq_layernorm_bwd(dy.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                    dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D, _stream()),
+        "vq_layernorm_bwd")
+    return dz, dgamma, dbeta
+
+
+def splice_overwrite(inputs_embeds: torch.Tensor, input_ids: torch.Tensor, features: torch.Tensor, image_id: int,
+                     overflow: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In-place training splice: inputs_embeds[b, pos:pos+n] = features[b] for every <image> position pos.
+
+    Mirrors src/models/vggt_qwen3_vlm.py:190-195 without the host `.nonzero()` sync.  `overflow` (optional int32
+    device scalar) counts spans that do not fit in the sequence (the reference raises in that case)."""
+    if not inputs_embeds.is_cuda:
+        raise RuntimeError("splice_overwrite: CUDA tensors only")
+    B, L, H = inputs_embeds.shape
+    assert inputs_embeds.is_contiguous() and input_ids.shape == (B, L) and features.shape[0] == B and features.shape[2] == H
+    ids = input_ids.to(torch.int64).contiguous()
+    feats = features.to(inputs_embeds.dtype).contiguous()
+    _lib.check(
+        _lib.lib().vq_splice_overwrite(inputs_embeds.data_ptr(), _dtype_code(inputs_embeds.dtype), ids.data_ptr(),
+                                       feats.data_ptr(), B, L, H, feats.shape[1], int(image_id), _ptr(overflow),
+                                       _stream()),
+        "vq_splice_overwrite")
+    return inputs_embeds
