@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Benchmark of the visual-encoding hot path (VGGT Aggregator + Perceiver projector), BASELINE.json's metric:
+encoded frames/s at N B200s, with the tensor-pipe roofline of the dominant kernel.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workloads (BASELINE.json `configs`, synthetic 518x518 inputs, random-init weights of the named architecture):
+  c2 (default) stage1_3d step shape: 8 single-view scenes per GPU, frozen VGGT aggregator forward +
+               Perceiver (perceiver_small) forward AND backward; N > 1 adds the Perceiver-gradient all-reduce
+               (config c5, weak scaling: 8 scenes per GPU).
+  c3           4 scenes x 8 frames, encode (forward) only.      c4   1 scene x 32 frames, encode only.
+
+One JSON line is printed by rank 0.  `value` = frames/s with inputs resident in HBM; `e2e` = the same step through
+the public module API (VGGTQwen3VLM.encode_images_trainable / encode_images) starting from pinned HOST images,
+including the H2D copy and a D2H read of the result.  `--impl reference` times the CPU oracle port of the
+reference path (oracle/, fp32 PyTorch on all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    "c2": dict(B=8, S=1, backward=True, desc="stage1_3d step: 8 x 1 view 518px, VGGT fwd + Perceiver fwd/bwd"),
+    "c3": dict(B=4, S=8, backward=False, desc="multi-view encode: 4 scenes x 8 frames 518px"),
+    "c4": dict(B=1, S=32, backward=False, desc="long multi-view encode: 1 scene x 32 frames 518px"),
+}
+NUM_VIS_TOKENS = 128   # configs/stage1_3d.yaml:5
+TEXT_HIDDEN = 2560     # Qwen3-4B hidden size
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (faster iteration)")
+    ap.add_argument("--profile-steps", type=int, default=2, help="instrumented steps for the per-kernel roofline")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ FLOP model
+def work_flops(wl: dict) -> dict:
+    """Algorithmic FLOPs per step per GPU (2MNK per GEMM, 4 Nq Nkv D per attention, no pruning credit)."""
+    from oracle.aggregator_ref import AggregatorConfig, aggregator_flops
+    from oracle.perceiver_ref import PerceiverShape, perceiver_flops
+
+    agg = aggregator_flops(AggregatorConfig(), wl["S"]) * wl["B"] * wl["S"]
+    perc = perceiver_flops(PerceiverShape(), NUM_VIS_TOKENS) * wl["B"] * (3.0 if wl["backward"] else 1.0)
+    return dict(aggregator=agg, perceiver=perc, total=agg + perc)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args) -> dict:
+    import torch
+    import torch.distributed as dist
+
+    from vggt_qwen3_b200 import _lib
+    from vggt_qwen3_b200.dist import BucketedGradAllReduce, attach_projector_allreduce, init_from_env
+    from vggt_qwen3_b200.projector_perceiver import PerceiverConfig
+    from vggt_qwen3_b200.vggt_qwen3_vlm import VGGTQwen3VLM, VisionLanguageConfig
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    rank, world, local = init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    wl = WORKLOADS[args.workload]
+    B, S, bwd = wl["B"], wl["S"], wl["backward"]
+    lib = _lib.lib()
+
+    # ---- model: random-init weights of the named architecture (no checkpoint, no network), seed 0
+    torch.manual_seed(0)
+
+    class _TextStub(torch.nn.Module):  # Qwen3-4B stays on stock PyTorch and is out of scope: only its hidden size matters
+        def __init__(self):
+            super().__init__()
+            self.config = type("C", (), {"hidden_size": TEXT_HIDDEN})()
+
+    class _TokStub:
+        def get_vocab(self):
+            return {"<image>": 0}
+
+        def convert_tokens_to_ids(self, t):
+            return 0
+
+    # perceiver_small.yaml; dropout sites are identity (eval-mode forward/backward), see DESIGN.md
+    pcfg = PerceiverConfig(latent_dim=4096, num_latents=128, num_heads=8, num_layers=6, ffn_dim=16384, dropout=0.1)
+    vcfg = VisionLanguageConfig(text_model_name="Qwen/Qwen3-4B-Instruct-2507", vision_ckpt_dir="/nonexistent",
+                                num_vis_tokens=NUM_VIS_TOKENS, geom_tokens=0, projector_cfg=pcfg)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = VGGTQwen3VLM(vcfg, text_model=_TextStub(), tokenizer=_TokStub())
+    model = model.to(dev).eval()
+    agg, proj = model.vision_model.aggregator, model.projector
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    images_host = torch.rand(B, S, 3, 518, 518, generator=gen).pin_memory()
+    images_dev = images_host.to(dev)
+    grad_out = torch.randn(B, NUM_VIS_TOKENS, TEXT_HIDDEN, generator=gen).to(dev) if bwd else None
+    result_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    reducer = None
+    finish_allreduce = lambda: None
+    if world > 1 and bwd:
+        reducer = BucketedGradAllReduce(grad_dtype=torch.bfloat16)
+        finish_allreduce = attach_projector_allreduce(proj, reducer)
+
+    def step_resident():
+        tokens = agg.encode_tokens(images_dev, NUM_VIS_TOKENS)
+        if bwd:
+            out = proj(tokens)
+            out.backward(grad_out)
+            finish_allreduce()
+            for p in proj.parameters():
+                p.grad = None
+        else:
+            with torch.no_grad():
+                out = proj(tokens)
+        return out
+
+    def step_e2e():
+        images_dev.copy_(images_host, non_blocking=True)                 # H2D of this step's inputs
+        if bwd:
+            out = model.encode_images_trainable(images_dev)
+            out.backward(grad_out)
+            finish_allreduce()
+            for p in proj.parameters():
+                p.grad = None
+        else:
+            out = model.encode_images(images_dev)
+        result_host.copy_(out.float().sum().reshape(1), non_blocking=True)  # D2H read of the step's result
+        torch.cuda.current_stream().synchronize()
+        return float(result_host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.vq_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, (lib.vq_launch_count() - n0) // steps
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop()
+    ms_e2e, _ = timed(step_e2e, max(3, args.steps // 2), 2)
+
+    frames = B * S * world
+    fl = work_flops(wl)
+    peaks = measured_peaks()
+
+    # ---- per-kernel roofline: instrumented repeat of the same steps (CUDA events around every launch, on the
+    # launch stream); kept out of the timed region above so the events do not perturb `value`.
+    roof, breakdown = None, {}
+    if rank == 0 and args.profile_steps > 0:
+        lib.vq_profile_enable(1)
+        for _ in range(args.profile_steps):
+            step_resident()
+        torch.cuda.synchronize()
+        buf = ctypes.create_string_buffer(1 << 20)
+        n = lib.vq_profile_dump(buf, len(buf))
+        lib.vq_profile_enable(0)
+        rows = []
+        for line in buf.value.decode().splitlines() if n else []:
+            kind, tag, m, nn, k, cnt, tms, tfl, tby = line.split()
+            rows.append(dict(kind=int(kind), tag=tag, m=int(m), n=int(nn), k=int(k), launches=int(cnt),
+                             ms=float(tms), flops=float(tfl), bytes=float(tby)))
+        total_ms = sum(r["ms"] for r in rows) or 1.0
+        for kind, name in ((0, "gemm"), (1, "attention"), (2, "row_kernels")):
+            rs = [r for r in rows if r["kind"] == kind]
+            t = sum(r["ms"] for r in rs)
+            if not rs:
+                continue
+            breakdown[name] = {"share_of_step": round(t / total_ms, 4), "ms_per_step": round(t / args.profile_steps, 4),
+                               "launches_per_step": sum(r["launches"] for r in rs) // args.profile_steps}
+            if kind < 2:
+                breakdown[name]["tflops"] = round(sum(r["flops"] for r in rs) / t / 1e9, 1)
+            else:
+                breakdown[name]["gbs"] = round(sum(r["bytes"] for r in rs) / t / 1e6, 1)
+        tensor_rows = [r for r in rows if r["kind"] < 2]
+        if tensor_rows:
+            top = max(tensor_rows, key=lambda r: r["ms"])
+            ach = top["flops"] / top["ms"] / 1e9
+            roof = {"bound": "tensor", "kernel": f"{top['tag']}[{top['m']}x{top['n']}x{top['k']}]",
+                    "achieved": round(ach, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": round(ach / peaks["tf_sustained"], 4), "peak_source": peaks["src"] + " (sustained)",
+                    "share_of_step": round(top["ms"] / total_ms, 4),
+                    "avg_launch_us": round(1e3 * top["ms"] / top["launches"], 2), "traffic": None}
+
+    out = {
+        "metric": "encoded frames/sec (VGGT Aggregator + Perceiver projector)",
+        "value": round(frames / (ms_step / 1e3), 2), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (uniform [0,1) 518x518 images, random-init weights of the named architecture, seed 0)",
+        "config": {
+            "workload": f"{args.workload}: {wl['desc']}", "scenes_per_gpu": B, "frames_per_scene": S,
+            "num_vis_tokens": NUM_VIS_TOKENS, "projector": "perceiver_small (4096/128 latents/8 heads/6 layers/16384)",
+            "projector_backward": bwd, "dropout": "identity (eval-mode forward/backward)",
+            "parallelism": f"dp{world} (scenes sharded, full replica per GPU" +
+                           (", bf16 Perceiver-grad all-reduce overlapped with backward)" if world > 1 and bwd else ")"),
+            "l2": "per-step working set (4.3 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush",
+        },
+        "algorithmic_tflop_per_step_per_gpu": round(fl["total"] / 1e12, 3),
+        "model_tflops_per_gpu": round(fl["total"] / (ms_step / 1e3) / 1e12, 1),
+        "frac_of_bf16_peak": {"measured_sustained": round(fl["total"] / (ms_step / 1e3) / 1e12 / peaks["tf_sustained"], 4),
+                              "nominal_2250": round(fl["total"] / (ms_step / 1e3) / 1e12 / 2250.0, 4)},
+        "clocks": clocks,
+        "e2e": {"value": round(frames / (ms_e2e / 1e3), 2), "unit": "frames/s", "ms_per_step": round(ms_e2e, 3),
+                "h2d_bytes_per_step": images_host.numel() * 4, "d2h_bytes_per_step": 4,
+                "api": "VGGTQwen3VLM.encode_images_trainable + backward" if bwd else "VGGTQwen3VLM.encode_images"},
+        "gpu_launches": int(launches) * args.steps,
+        "gpu_launches_per_step": int(launches),
+        "roofline": roof,
+        "kernel_breakdown": breakdown,
+    }
+    if reducer is not None:
+        out["allreduce_bytes_per_step"] = reducer.bytes_reduced // max(1, (args.steps + max(args.warmup, 3)
+                                                                         + max(3, args.steps // 2) + 2 + args.profile_steps))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_reference(wl, steps=1, warmup=0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out if rank == 0 else {}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference(wl: dict, steps: int, warmup: int) -> dict:
+    """The reference path on the host cores: fp32 PyTorch oracle port (oracle/: the upstream `vggt` package is not
+    vendored and a Python reference cannot travel to the GPU box).  One step = ONE frame of the aggregator (S = 1, or
+    a 2-frame scene for the multi-view workloads) + the Perceiver for one sample, with `d` of the 24 stem blocks /
+    aggregator iterations and `l` of the 6 Perceiver layers actually executed and the time scaled by 24/d and 6/l
+    (identical blocks), so that warmup + steps stays within a few minutes."""
+    import torch
+
+    from oracle import aggregator_ref as A
+    from oracle import perceiver_ref as P
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_exec = steps + warmup
+    d = 24 if n_exec <= 2 else max(1, min(24, 48 // n_exec))
+    l = 6 if n_exec <= 2 else max(1, min(6, 12 // n_exec))
+    S = 1 if wl["S"] == 1 else 2
+    cfg = A.AggregatorConfig(depth=d, stem_depth=d)
+    state = A.init_aggregator_state(cfg, 0)
+    shape = P.PerceiverShape(num_layers=l)
+    pstate = P.init_perceiver_state(shape, 0)
+    img = torch.rand(1, S, 3, 518, 518, generator=torch.Generator().manual_seed(0))
+    go = torch.randn(1, shape.num_latents, shape.out_dim, generator=torch.Generator().manual_seed(1))
+
+    def one():
+        t0 = time.perf_counter()
+        outs, _ = A.aggregator_forward(state, img, cfg, return_all=False)
+        t1 = time.perf_counter()
+        tok = P.select_vis_tokens(outs[-1], NUM_VIS_TOKENS)
+        if wl["backward"]:
+            leaf = {k: v.requires_grad_(True) for k, v in pstate.items()}
+            out = P.perceiver_forward(leaf, tok, shape.num_heads)
+            out.backward(go)
+            for v in pstate.values():
+                v.grad = None
+        else:
+            with torch.no_grad():
+                P.perceiver_forward(pstate, tok, shape.num_heads)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    for _ in range(warmup):
+        one()
+    t_agg = t_perc = 0.0
+    for _ in range(steps):
+        a, p = one()
+        t_agg += a
+        t_perc += p
+    t_agg, t_perc = t_agg / steps, t_perc / steps
+    # scale the sampled blocks to the full depth; the Perceiver serves one sample = S_workload frames
+    per_scene = t_agg * (24.0 / d) * (wl["S"] / S) + t_perc * (6.0 / l)
+    fps = wl["S"] / per_scene
+    return {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of 1 scene x {S} frame(s) 518px fp32: {d}/24 stem blocks + {d}/24 frame+global "
+                      f"iterations + {l}/6 Perceiver layers ({'fwd+bwd' if wl['backward'] else 'fwd'}) executed, time scaled "
+                      f"to full depth and to {wl['S']} frame(s) per scene",
+            "seconds_per_sample": round(t_agg + t_perc, 3)}
+
+
+def run_reference(args) -> dict:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return {}
+    wl = WORKLOADS[args.workload]
+    t0 = time.perf_counter()
+    base = cpu_reference(wl, steps=args.steps, warmup=args.warmup)
+    frames_per_step = wl["B"] * wl["S"]
+    ms = 1e3 * frames_per_step / base["value"]
+    return {
+        "impl": "reference",
+        "metric": "encoded frames/sec (VGGT Aggregator + Perceiver projector)",
+        "value": base["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (uniform [0,1) 518x518 images, random-init weights of the named architecture, seed 0)",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "scenes_per_gpu": wl["B"], "frames_per_scene": wl["S"],
+                   "num_vis_tokens": NUM_VIS_TOKENS, "projector_backward": wl["backward"],
+                   "note": "reference path on host cores: fp32 PyTorch oracle port; ms_per_step extrapolated from the sample"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_seconds": round(time.perf_counter() - t0, 1),
+    }
+
+
+def main():
+    args = parse_args()
+    out = run_reference(args) if args.impl == "reference" else run_b200(args)
+    if out:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,14 @@ const char* vq_last_error(void);
 int vq_version(void);
 /* Number of SMs of the current device (148 on B200); used to size persistent grids. */
 int vq_num_sms(void);
+/* Launch accounting: total kernels launched by this library so far (monotonic). */
+long long vq_launch_count(void);
+/* Optional CUDA-event profiling: enable(1) starts a fresh recording in which every launch is bracketed by two
+ * events on its stream; dump() synchronises on them and writes one text line per (kind, tag, m, n, k):
+ * "kind tag m n k launches total_ms total_flops total_bytes" (kind 0 = GEMM, 1 = attention, 2 = row kernel).
+ * Returns bytes written, 0 if `cap` is too small. */
+int vq_profile_enable(int on);
+long long vq_profile_dump(char* buf, long long cap);
 
 /* ------------------------------------------------------------------------------------------------
  * vq_gemm — C[M,N] = epilogue(A[M,K] * B[N,K]^T), bf16 inputs, fp32 accumulation in TMEM.

@@ -145,6 +145,12 @@ def _declare(lib: C.CDLL) -> None:
     lib.vq_attention_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.vq_aggregator_workspace_bytes.restype = C.c_size_t
     lib.vq_aggregator_workspace_bytes.argtypes = [C.POINTER(AggregatorCfg)]
+    lib.vq_launch_count.restype = C.c_longlong
+    lib.vq_launch_count.argtypes = []
+    lib.vq_profile_enable.restype = C.c_int
+    lib.vq_profile_enable.argtypes = [C.c_int]
+    lib.vq_profile_dump.restype = C.c_longlong
+    lib.vq_profile_dump.argtypes = [C.c_char_p, C.c_longlong]
     for name in ("vq_perceiver_saved_bytes", "vq_perceiver_workspace_bytes"):
         getattr(lib, name).restype = C.c_size_t
         getattr(lib, name).argtypes = [C.POINTER(PerceiverCfg)]

@@ -291,7 +291,12 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
   g.heads = heads;
   g.n_kv_tiles = (seq_len + kTileKV - 1) / kTileKV;
   dim3 grid((seq_len + 2 * kTileQ - 1) / (2 * kTileQ), heads, n_seq);
-  attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(*tm, g);
+  {
+    const double flops = 4.0 * n_seq * heads * (double)seq_len * seq_len * kHeadDim;
+    const double bytes = 2.0 * (double)rows * HD * 4.0;  // q, k, v read once + out written (bf16)
+    LaunchScope scope(kKindAttention, "attention_fwd", n_seq, seq_len, heads, flops, bytes, stream);
+    attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(*tm, g);
+  }
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
 }

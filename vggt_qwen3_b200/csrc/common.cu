@@ -98,9 +98,97 @@ int num_sms() {
   return n;
 }
 
+// ------------------------------------------------------------------ launch accounting / profiling
+struct ProfRecord {
+  int kind;
+  const char* tag;
+  int m, n, k;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static long long g_launches = 0;
+
+static cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+LaunchScope::LaunchScope(int kind, const char* tag, int m, int n, int k, double flops, double bytes,
+                         cudaStream_t stream)
+    : slot_(-1), stream_(stream) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  ++g_launches;
+  if (!g_prof_on) return;
+  ProfRecord r{kind, tag, m, n, k, flops, bytes, take_event(), take_event()};
+  cudaEventRecord(r.e0, stream);
+  slot_ = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+LaunchScope::~LaunchScope() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  cudaEventRecord(g_prof[slot_].e1, stream_);
+}
+
 }  // namespace vq
 
 extern "C" {
+int vq_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(vq::g_prof_mu);
+  for (auto& r : vq::g_prof) {
+    vq::g_event_pool.push_back(r.e0);
+    vq::g_event_pool.push_back(r.e1);
+  }
+  vq::g_prof.clear();
+  vq::g_prof_on = on != 0;
+  return VQ_OK;
+}
+long long vq_launch_count(void) {
+  std::lock_guard<std::mutex> lock(vq::g_prof_mu);
+  return vq::g_launches;
+}
+// Text table of the recorded launches aggregated by (kind, tag, m, n, k):
+//   kind tag m n k launches total_ms total_flops total_bytes
+// Synchronises on the recorded events.  Returns the number of bytes written (0 if buf too small).
+long long vq_profile_dump(char* buf, long long cap) {
+  std::lock_guard<std::mutex> lock(vq::g_prof_mu);
+  struct Agg { int kind; const char* tag; int m, n, k; long long cnt; double ms, flops, bytes; };
+  std::vector<Agg> aggs;
+  for (auto& r : vq::g_prof) {
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    Agg* a = nullptr;
+    for (auto& x : aggs)
+      if (x.kind == r.kind && x.tag == r.tag && x.m == r.m && x.n == r.n && x.k == r.k) { a = &x; break; }
+    if (!a) {
+      aggs.push_back(Agg{r.kind, r.tag, r.m, r.n, r.k, 0, 0, 0, 0});
+      a = &aggs.back();
+    }
+    a->cnt += 1; a->ms += ms; a->flops += r.flops; a->bytes += r.bytes;
+  }
+  std::string out;
+  char line[256];
+  for (auto& a : aggs) {
+    snprintf(line, sizeof(line), "%d %s %d %d %d %lld %.6f %.6e %.6e\n", a.kind, a.tag, a.m, a.n, a.k, a.cnt, a.ms,
+             a.flops, a.bytes);
+    out += line;
+  }
+  if ((long long)out.size() + 1 > cap) return 0;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (long long)out.size();
+}
+
 const char* vq_last_error(void) { return vq::g_last_error.c_str(); }
 int vq_version(void) { return 1; }
 int vq_num_sms(void) { return vq::num_sms(); }

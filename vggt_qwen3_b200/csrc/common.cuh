@@ -38,4 +38,15 @@ const CUtensorMap* get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t o
 
 int num_sms();
 
+// Launch accounting + optional CUDA-event profiling of every kernel the library launches.
+// Always counts launches; when profiling is enabled (vq_profile_enable) it brackets the launch with
+// two events on the launch stream and records (kind, tag, shape, algorithmic flops / bytes).
+enum LaunchKind { kKindGemm = 0, kKindAttention = 1, kKindRow = 2, kNumKinds = 3 };
+struct LaunchScope {
+  LaunchScope(int kind, const char* tag, int m, int n, int k, double flops, double bytes, cudaStream_t stream);
+  ~LaunchScope();
+  int slot_;
+  cudaStream_t stream_;
+};
+
 }  // namespace vq

@@ -397,7 +397,15 @@ static int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs&
     configured = true;
   }
   int grid = g.total_tiles < num_sms() ? g.total_tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*tmA, *tmB, g);
+  {
+    static const char* const kTags[] = {"gemm_linear", "gemm_gelu", "gemm_gelu_bwd", "gemm_qkv_rope", "gemm_patch"};
+    const double Z = (double)g.total_tiles / ((double)g.m_tiles * g.n_tiles);
+    const double mnk = (double)g.M * g.N * g.K;
+    const double bytes = Z * (2.0 * ((double)g.M * g.K + (double)g.N * g.K) +
+                              (OUT_F32 ? 4.0 : 2.0) * (double)g.M * g.N * (g.add ? 2.0 : 1.0));
+    LaunchScope scope(kKindGemm, kTags[MODE], g.M, g.N, g.K, 2.0 * mnk * Z, bytes, stream);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*tmA, *tmB, g);
+  }
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
 }

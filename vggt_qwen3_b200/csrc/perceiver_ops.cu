@@ -217,6 +217,7 @@ extern "C" int vq_softmax_fwd(const float* scores, void* probs_bf16, int64_t row
   VQ_CHECK_ARG(scores && probs_bf16, "null pointer");
   VQ_CHECK_ARG(rows > 0 && T > 0 && T <= 32 * kMaxPerLane && Tp >= T && Tp <= 32 * kMaxPerLane && ld_scores >= T,
                "softmax geometry (T <= 1024)");
+  LaunchScope scope(kKindRow, "softmax_fwd", (int)rows, T, 0, 0, (double)rows * (T * 4.0 + Tp * 2.0), stream);
   softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
       scores, reinterpret_cast<__nv_bfloat16*>(probs_bf16), rows, T, ld_scores, Tp);
   VQ_CHECK_CUDA(cudaGetLastError());
@@ -228,6 +229,7 @@ extern "C" int vq_softmax_bwd(const void* probs_bf16, const float* dprobs, void*
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(probs_bf16 && dprobs && dscores_bf16, "null pointer");
   VQ_CHECK_ARG(rows > 0 && T > 0 && Tp >= T && Tp <= 32 * kMaxPerLane && ld_dprobs >= T, "softmax geometry");
+  LaunchScope scope(kKindRow, "softmax_bwd", (int)rows, T, 0, 0, (double)rows * (T * 6.0 + Tp * 2.0), stream);
   softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(probs_bf16), dprobs, reinterpret_cast<__nv_bfloat16*>(dscores_bf16),
       rows, T, ld_dprobs, Tp, scale);
@@ -247,6 +249,7 @@ extern "C" int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const f
   const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(z_bf16);
   __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(dz_bf16);
+  LaunchScope scope(kKindRow, "layernorm_bwd", (int)rows, D, 0, 0, (double)rows * D * 6.0, stream);
 #define VQ_LNB_CASE(V)                                                                                         \
   case V:                                                                                                      \
     layernorm_bwd_kernel<V><<<grid, 256, smem, stream>>>(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, rows, D, \
@@ -269,6 +272,7 @@ extern "C" int vq_colsum(const void* x, int32_t dtype, float* out, int64_t rows,
   VQ_CHECK_ARG(x && out && rows > 0 && N > 0 && ld >= N, "colsum arguments");
   const int rows_per_cta = 64;
   dim3 grid((N + 255) / 256, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
+  LaunchScope scope(kKindRow, "colsum", (int)rows, N, 0, 0, (double)rows * N * (dtype == VQ_F32 ? 4.0 : 2.0), stream);
   if (dtype == VQ_F32) colsum_kernel<true><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
   else colsum_kernel<false><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
   VQ_CHECK_CUDA(cudaGetLastError());
@@ -282,6 +286,7 @@ extern "C" int vq_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, vq_s
                "cast: 16-byte alignment");
   const long long n8 = n / 8;
   const long long threads = n8 > 0 ? n8 : 1;
+  LaunchScope scope(kKindRow, "cast_f32_bf16", 0, 0, 0, 0, (double)n * 6.0, stream);
   cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
       in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n8, n);
   VQ_CHECK_CUDA(cudaGetLastError());
@@ -292,6 +297,7 @@ extern "C" int vq_broadcast_rows(const void* src_bf16, void* out_bf16, int64_t n
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(src_bf16 && out_bf16 && n > 0 && n % 8 == 0 && B > 0, "broadcast arguments (n % 8 == 0)");
   const long long n16 = n / 8;
+  LaunchScope scope(kKindRow, "broadcast_rows", B, 0, 0, 0, (double)n * 2.0 * (1 + B), stream);
   broadcast_rows_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(src_bf16), reinterpret_cast<uint4*>(out_bf16), n16, B);
   VQ_CHECK_CUDA(cudaGetLastError());
@@ -303,6 +309,7 @@ extern "C" int vq_reduce_batch(const void* in_bf16, float* out, int64_t n, int32
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(in_bf16 && out && n > 0 && n % 2 == 0 && B > 0, "reduce_batch arguments (n even)");
   const long long threads = n / 2;
+  LaunchScope scope(kKindRow, "reduce_batch", B, 0, 0, 0, (double)n * (2.0 * B + 4.0), stream);
   reduce_batch_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(in_bf16), out, n, B, accumulate);
   VQ_CHECK_CUDA(cudaGetLastError());

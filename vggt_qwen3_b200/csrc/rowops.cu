@@ -241,6 +241,7 @@ extern "C" int vq_im2col_patches(const float* images, void* out_bf16, int32_t fr
     VQ_CHECK_CUDA(cudaFuncSetAttribute(im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  LaunchScope scope(kKindRow, "im2col", frames, H, W, 0, (double)frames * (3.0 * H * W * 4 + (double)gh * gw * Kp * 2), stream);
   im2col_kernel<<<frames * gh, 256, smem, stream>>>(images, reinterpret_cast<__nv_bfloat16*>(out_bf16), H, W, patch,
                                                     gh, gw, Kp);
   VQ_CHECK_CUDA(cudaGetLastError());
@@ -253,6 +254,7 @@ extern "C" int vq_init_special_tokens(float* x, const float* cls_token, const fl
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(x && cls_token && pos_embed0 && register_tokens, "null pointer");
   VQ_CHECK_ARG(frames > 0 && P >= n_special && n_special >= 1, "token geometry");
+  LaunchScope scope(kKindRow, "init_special", frames, n_special, D, 0, (double)frames * n_special * D * 4, stream);
   init_special_kernel<<<frames, 256, 0, stream>>>(x, cls_token, pos_embed0, register_tokens, P, D, n_special);
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
@@ -263,6 +265,7 @@ static int launch_ln(const void* in, void* out, const float* gamma, const float*
                      float eps, float* mean_out, float* rstd_out, cudaStream_t stream) {
   const int warps = 8;
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  LaunchScope scope(kKindRow, "layernorm", (int)rows, D, 0, 0, (double)rows * D * ((IN_F32 ? 4 : 2) + (OUT_F32 ? 4 : 2)), stream);
 #define VQ_LN_CASE(V)                                                                                      \
   case V:                                                                                                  \
     layernorm_kernel<V, IN_F32, OUT_F32><<<grid, warps * 32, 0, stream>>>(in, out, gamma, beta, rows, D, eps, \
@@ -302,6 +305,7 @@ extern "C" int vq_stem_finalize(float* x, const float* gamma, const float* beta,
   VQ_CHECK_ARG(rows > 0 && D % 128 == 0 && P > n_special && S > 0, "geometry");
   const int warps = 8;
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  LaunchScope scope(kKindRow, "stem_finalize", (int)rows, D, 0, 0, (double)rows * D * 8, stream);
 #define VQ_SF_CASE(V)                                                                                       \
   case V:                                                                                                   \
     stem_finalize_kernel<V><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, camera_token, register_token, rows, \
@@ -326,6 +330,7 @@ extern "C" int vq_gather_tokens(const float* x, void* out_bf16, int32_t B, int64
   VQ_CHECK_ARG(out_ld % 4 == 0 && col_off % 4 == 0 && col_off + D <= out_ld, "output layout");
   const long long total = (long long)B * n_take;
   const int warps = 8;
+  LaunchScope scope(kKindRow, "gather_tokens", B, n_take, D, 0, (double)total * D * 6, stream);
   gather_tokens_kernel<<<(unsigned)((total + warps - 1) / warps), warps * 32, 0, stream>>>(
       x, reinterpret_cast<__nv_bfloat16*>(out_bf16), D, tokens_per_scene, n_take, out_ld, col_off, total);
   VQ_CHECK_CUDA(cudaGetLastError());
@@ -345,6 +350,7 @@ extern "C" int vq_splice_overwrite(void* inputs_embeds, int32_t dtype, const int
   const long long total = (long long)B * L;
   const int warps = 8;
   const unsigned grid = (unsigned)((total + warps - 1) / warps);
+  LaunchScope scope(kKindRow, "splice_overwrite", B, L, n_feat, 0, (double)B * n_feat * hidden * elt * 2, stream);
   if (dtype == VQ_F32)
     splice_overwrite_kernel<float><<<grid, warps * 32, 0, stream>>>(
         reinterpret_cast<float*>(inputs_embeds), reinterpret_cast<const long long*>(input_ids),
