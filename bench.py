@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (faster iteration)")
     ap.add_argument("--profile-steps", type=int, default=2, help="instrumented steps for the per-kernel roofline")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel event-timing table (text) to this path")
     return ap.parse_args()
 
 
@@ -248,6 +249,14 @@ def run_b200(args) -> dict:
             rows.append(dict(kind=int(kind), tag=tag, m=int(m), n=int(nn), k=int(k), launches=int(cnt),
                              ms=float(tms), flops=float(tfl), bytes=float(tby)))
         total_ms = sum(r["ms"] for r in rows) or 1.0
+        if args.profile_out:
+            with open(args.profile_out, "w") as fh:
+                fh.write(f"# per-kernel CUDA-event timing over {args.profile_steps} instrumented step(s), workload {args.workload}\n")
+                fh.write("# kind tag m n k launches total_ms avg_us share TFLOP/s GB/s\n")
+                for r in sorted(rows, key=lambda r: -r["ms"]):
+                    fh.write(f"{r['kind']} {r['tag']} {r['m']} {r['n']} {r['k']} {r['launches']} {r['ms']:.4f} "
+                             f"{1e3 * r['ms'] / r['launches']:.2f} {r['ms'] / total_ms:.4f} "
+                             f"{r['flops'] / r['ms'] / 1e9:.1f} {r['bytes'] / r['ms'] / 1e6:.1f}\n")
         for kind, name in ((0, "gemm"), (1, "attention"), (2, "row_kernels")):
             rs = [r for r in rows if r["kind"] == kind]
             t = sum(r["ms"] for r in rs)

@@ -109,6 +109,7 @@ typedef struct vq_gemm_desc {
   float qk_eps;
   float q_scale;                     /* folded softmax scale: log2(e)/sqrt(64) */
   const float *rope_cos, *rope_sin;  /* [max_pos+1][16], position 0 = identity */
+  int32_t rope_positions;            /* rows of the rope tables (max_pos + 1); 0 = unknown (tables read from global) */
   int32_t n_patches;                 /* VQ_EPI_PATCH: gh*gw */
   const float* pos_embed;            /* VQ_EPI_PATCH: [(1+n_patches), N] f32 */
 } vq_gemm_desc;

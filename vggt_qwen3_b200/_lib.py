@@ -42,6 +42,7 @@ class GemmDesc(C.Structure):
         ("qn_w", _f32p), ("qn_b", _f32p), ("kn_w", _f32p), ("kn_b", _f32p),
         ("qk_eps", C.c_float), ("q_scale", C.c_float),
         ("rope_cos", _f32p), ("rope_sin", _f32p),
+        ("rope_positions", C.c_int32),
         ("n_patches", C.c_int32),
         ("pos_embed", _f32p),
     ]

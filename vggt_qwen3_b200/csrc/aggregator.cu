@@ -90,7 +90,7 @@ int run_block(const vq_aggregator_cfg* c, const vq_block_weights& bw, const vq_a
     g.qn_w = bw.q_norm_w; g.qn_b = bw.q_norm_b; g.kn_w = bw.k_norm_w; g.kn_b = bw.k_norm_b;
     g.qk_eps = c->qk_eps;
     g.q_scale = 1.4426950408889634f / 8.0f;
-    g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin;
+    g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_positions = w->rope_max_pos + 1;
     rc = vq_gemm(&g, stream);
     if (rc) return rc;
   }

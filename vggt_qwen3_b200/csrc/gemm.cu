@@ -17,7 +17,8 @@ namespace vq {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;     // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kRopeSmemPos = 64;       // rope table positions staged in smem (larger tables are read from global)
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 
 struct GemmArgs {
@@ -42,6 +43,7 @@ struct GemmArgs {
   const float *qn_w, *qn_b, *kn_w, *kn_b;
   float qk_eps, q_scale;
   const float *rope_cos, *rope_sin;
+  int rope_positions;  // rows of the rope tables (max_pos + 1), 0 if unknown
   int n_patches;
   const float* pos_embed;
 };
@@ -52,7 +54,9 @@ struct GemmCfg {
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 / 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // per-warp [bias|gamma] vectors (8 warps x BLOCK_N floats), q/k-norm affine (4 x 64), rope cos/sin tables
+  static constexpr int kEpiVecBytes = 8 * BLOCK_N * 4 + 4 * 64 * 4 + 2 * kRopeSmemPos * 16 * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiVecBytes;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -116,6 +120,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_slot = bar_tempty + 16;
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* epi_vec = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
+  float* qk_vec = epi_vec + 8 * BLOCK_N;        // [q_w | q_b | k_w | k_b] x 64
+  float* rope_vec = qk_vec + 4 * 64;            // [cos | sin] x kRopeSmemPos x 16
+  const bool rope_in_smem = g.rope_positions > 0 && g.rope_positions <= kRopeSmemPos;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -129,13 +137,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 128);
+      mbar_init(bar_tempty + 8 * s, 256);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
+  }
+  if constexpr (MODE == VQ_EPI_QKV_ROPE) {
+    if (g.apply_qknorm_rope) {
+      for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        qk_vec[i] = g.qn_w[i]; qk_vec[64 + i] = g.qn_b[i];
+        qk_vec[128 + i] = g.kn_w[i]; qk_vec[192 + i] = g.kn_b[i];
+      }
+      if (rope_in_smem) {
+        for (int i = threadIdx.x; i < g.rope_positions * 16; i += blockDim.x) {
+          rope_vec[i] = g.rope_cos[i];
+          rope_vec[kRopeSmemPos * 16 + i] = g.rope_sin[i];
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -220,9 +242,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps share each TMEM lane quarter (hardware: warp w may touch lanes 32*(w%4)..+31) and split the
+    // tile's columns in halves; one accumulator row per thread.  Per-column vectors (bias, LayerScale gamma)
+    // are staged per warp in smem before the accumulator is waited for, TMEM loads are double-buffered and all
+    // global loads of a 32-column chunk are issued before its math, so no latency sits on the critical path.
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kHalfN = BLOCK_N / 2;
     const int row_in_tile = quarter * 32 + lane;
+    float* my_vec = epi_vec + (warp - 2) * (2 * kHalfN);  // [bias | gamma] x kHalfN, private to this warp
     int it = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
       const int z = tile / tiles_per_z;
@@ -233,43 +262,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long c_r = z0 * g.c_r0 + z1 * g.c_r1, c_c = z0 * g.c_c0 + z1 * g.c_c1;
       const int as = it & 1;
       const uint32_t as_phase = (it >> 1) & 1;
+      const int n_base = n_blk * BLOCK_N + half * kHalfN;  // first column this warp owns
+
+      // stage bias / gamma for this warp's columns (overlaps the wait for the accumulator)
+      __syncwarp();
+      for (int c = lane * 4; c < kHalfN; c += 128) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f), gm = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (n_base + c < g.N) {
+          if (g.bias) b = __ldg(reinterpret_cast<const float4*>(g.bias + n_base + c));
+          if (g.gamma) gm = __ldg(reinterpret_cast<const float4*>(g.gamma + n_base + c));
+        }
+        *reinterpret_cast<float4*>(my_vec + c) = b;
+        *reinterpret_cast<float4*>(my_vec + kHalfN + c) = gm;
+      }
+      __syncwarp();
+
       mbar_wait(bar_tfull + 8 * as, as_phase);
       tc_fence_after();
 
       const int m = m_blk * kBlockM + row_in_tile;
       const bool row_ok = m < g.M;
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N + half * kHalfN;
 
       if constexpr (MODE == VQ_EPI_QKV_ROPE) {
         // One head (64 columns) at a time; the whole head row lives in this thread's registers.
+        static_assert(kHalfN == 64, "QKV epilogue: one head per warp per tile");
         const int D3 = g.N / 3;  // q | k | v column blocks
-        int pos_y = 0, pos_x = 0;
-        {
-          const int p = m % g.tokens_per_frame;
-          if (p >= g.patch_start) {
-            const int idx = p - g.patch_start;
-            pos_y = idx / g.grid_w + 1;
-            pos_x = idx % g.grid_w + 1;
-          }
-        }
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 64) {
-          const int n0 = n_blk * BLOCK_N + c;
-          if (n0 >= g.N) break;
-          uint32_t r0[32], r1[32];
-          tmem_ld32(taddr + c, r0);
-          tmem_ld32(taddr + c + 32, r1);
-          tmem_wait_ld();
+        if (n_base < g.N) {
           float v[64];
+          {
+            uint32_t r[32];
+            tmem_ld32(taddr, r);
+            tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = __uint_as_float(r0[i]) + __ldg(g.bias + n0 + i);
-            v[32 + i] = __uint_as_float(r1[i]) + __ldg(g.bias + n0 + 32 + i);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + my_vec[i];
+            tmem_ld32(taddr + 32, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]) + my_vec[32 + i];
           }
-          const int which = n0 / D3;  // 0 = q, 1 = k, 2 = v
+          const int which = n_base / D3;  // 0 = q, 1 = k, 2 = v
           if (which < 2 && g.apply_qknorm_rope) {
-            const float* w = which == 0 ? g.qn_w : g.kn_w;
-            const float* b = which == 0 ? g.qn_b : g.kn_b;
+            const float* w = qk_vec + which * 128;  // [w | b] of q_norm or k_norm
             float mean = 0.f;
 #pragma unroll
             for (int i = 0; i < 64; ++i) mean += v[i];
@@ -282,19 +316,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             const float rstd = rsqrtf(var * (1.0f / 64.0f) + g.qk_eps);
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+            for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * w[i] + w[64 + i];
             // 2-D RoPE: dims [0,32) rotate with the row (y) position, [32,64) with the column (x).
+            int pos_y = 0, pos_x = 0;
+            const int p = m % g.tokens_per_frame;
+            if (p >= g.patch_start) {
+              const int idx = p - g.patch_start;
+              pos_y = idx / g.grid_w + 1;
+              pos_x = idx % g.grid_w + 1;
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int pos = h == 0 ? pos_y : pos_x;
-              const float* cs = g.rope_cos + pos * 16;
-              const float* sn = g.rope_sin + pos * 16;
+              float co[16], si[16];
+              if (rope_in_smem) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 c4 = *reinterpret_cast<const float4*>(rope_vec + pos * 16 + j);
+                  const float4 s4 = *reinterpret_cast<const float4*>(rope_vec + kRopeSmemPos * 16 + pos * 16 + j);
+                  co[j] = c4.x; co[j + 1] = c4.y; co[j + 2] = c4.z; co[j + 3] = c4.w;
+                  si[j] = s4.x; si[j + 1] = s4.y; si[j + 2] = s4.z; si[j + 3] = s4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  co[j] = __ldg(g.rope_cos + pos * 16 + j);
+                  si[j] = __ldg(g.rope_sin + pos * 16 + j);
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float co = __ldg(cs + j), si = __ldg(sn + j);
                 const float a = v[32 * h + j], b2 = v[32 * h + 16 + j];
-                v[32 * h + j] = a * co - b2 * si;
-                v[32 * h + 16 + j] = b2 * co + a * si;
+                v[32 * h + j] = a * co[j] - b2 * si[j];
+                v[32 * h + 16 + j] = b2 * co[j] + a * si[j];
               }
             }
           }
@@ -303,7 +357,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int i = 0; i < 64; ++i) v[i] *= g.q_scale;
           }
           if (row_ok) {
-            const long long off = (c_r + m) * g.ldc + c_c + n0;
+            const long long off = (c_r + m) * g.ldc + c_c + n_base;
 #pragma unroll
             for (int i = 0; i < 64; i += 8) store8<OUT_F32>(g.C, off + i, v + i);
           }
@@ -317,57 +371,67 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           out_row = (long long)f * g.tokens_per_frame + g.patch_start + idx;
           pe_row = g.pos_embed + (long long)(1 + idx) * g.N;
         }
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          const int n0 = n_blk * BLOCK_N + c;
-          if (n0 >= g.N) break;
-          uint32_t r[32];
-          tmem_ld32(taddr + c, r);
+        const long long io_row = c_r + m;
+        constexpr int kChunks = kHalfN / 32;
+        uint32_t acc[2][32];
+        if (n_base < g.N) tmem_ld32(taddr, acc[0]);
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+          const int n0 = n_base + ch * 32;
+          if (n0 >= g.N) break;  // warp-uniform
           tmem_wait_ld();
+          if (ch + 1 < kChunks && n0 + 32 < g.N) tmem_ld32(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);
+          const uint32_t(&r)[32] = acc[ch & 1];
+          const int groups = min(4, (g.N - n0) >> 3);  // valid 8-column groups in this chunk
+          // ---- issue every global load of the chunk first
+          float addv[32];
+          float auxv[32];
+          if (g.add) {
 #pragma unroll
-          for (int i8 = 0; i8 < 32; i8 += 8) {
-            const int n = n0 + i8;
-            if (n >= g.N) break;  // N is a multiple of 8
+            for (int q = 0; q < 4; ++q)
+              if (row_ok && q < groups) load8<OUT_F32>(g.add, io_row * g.ldadd + c_c + n0 + q * 8, addv + q * 8);
+          }
+          if constexpr (MODE == VQ_EPI_GELU_BWD) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (row_ok && q < groups) load8<false>(g.aux, io_row * g.ldaux + c_c + n0 + q * 8, auxv + q * 8);
+          }
+          if constexpr (MODE == VQ_EPI_PATCH) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (row_ok && q < groups) load8<true>(pe_row, n0 + q * 8, auxv + q * 8);
+          }
+          // ---- math + store, 8 columns at a time
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
             float v[8];
+            const float* bv = my_vec + ch * 32 + q * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i8 + i]) * g.alpha;
-            if (g.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + 1);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (!row_ok) continue;
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q * 8 + i]) * g.alpha + bv[i];
+            if (!(row_ok && q < groups)) continue;
             if constexpr (MODE == VQ_EPI_GELU) {
-              if (g.aux) store8<false>(g.aux, (c_r + m) * g.ldaux + c_c + n, v);
+              if (g.aux) store8<false>(g.aux, io_row * g.ldaux + c_c + n0 + q * 8, v);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
             }
             if constexpr (MODE == VQ_EPI_GELU_BWD) {
-              float pre[8];
-              load8<false>(g.aux, (c_r + m) * g.ldaux + c_c + n, pre);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(pre[i]);
+              for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(auxv[q * 8 + i]);
             }
             if constexpr (MODE == VQ_EPI_PATCH) {
-              const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe_row + n));
-              const float4 p1 = __ldg(reinterpret_cast<const float4*>(pe_row + n) + 1);
-              v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
-              v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += auxv[q * 8 + i];
             }
             if (g.gamma) {
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(g.gamma + n));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gamma + n) + 1);
-              v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-              v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+              const float* gv = my_vec + kHalfN + ch * 32 + q * 8;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= gv[i];
             }
             if (g.add) {
-              float a[8];
-              load8<OUT_F32>(g.add, (c_r + m) * g.ldadd + c_c + n, a);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += a[i];
+              for (int i = 0; i < 8; ++i) v[i] += addv[q * 8 + i];
             }
-            store8<OUT_F32>(g.C, out_row * g.ldc + c_c + n, v);
+            store8<OUT_F32>(g.C, out_row * g.ldc + c_c + n0 + q * 8, v);
           }
         }
       }
@@ -496,6 +560,7 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
   g.qn_w = d->qn_w; g.qn_b = d->qn_b; g.kn_w = d->kn_w; g.kn_b = d->kn_b;
   g.qk_eps = d->qk_eps; g.q_scale = d->q_scale == 0.f ? 1.f : d->q_scale;
   g.rope_cos = d->rope_cos; g.rope_sin = d->rope_sin;
+  g.rope_positions = d->rope_positions;
   g.n_patches = d->n_patches; g.pos_embed = d->pos_embed;
 
   const bool f32 = d->c_dtype == VQ_F32;

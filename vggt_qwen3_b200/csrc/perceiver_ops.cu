@@ -75,94 +75,110 @@ softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict_
   }
 }
 
-// ---- LayerNorm backward.  dz = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)), xhat = (z - mean) * rstd.
-// One warp per row for dz; per-CTA column partials of dgamma (sum dy*xhat) and dbeta (sum dy) are reduced in smem
-// over the CTA's rows and added to the f32 outputs with one atomic per column per CTA.
+// ---- LayerNorm backward, two HBM-bound kernels.
+// (1) dz = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)), xhat = (z - mean) * rstd: one warp per row.
 template <int VEC>
 __global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
-                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dz,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int D,
-                     int rows_per_cta) {
-  extern __shared__ float red[];  // [2][D]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  float accg[VEC][4], accb[VEC][4];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) accg[i][j] = accb[i][j] = 0.f;
-
-  const long long row0 = (long long)blockIdx.x * rows_per_cta;
-  for (int rr = warp; rr < rows_per_cta; rr += nwarps) {
-    const long long r = row0 + rr;
-    if (r >= rows) break;
-    const float mu = mean[r], rs = rstd[r];
-    float dyv[VEC][4], xh[VEC][4];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int col = (i * 32 + lane) * 4;
-      const uint2 a = *reinterpret_cast<const uint2*>(dy + r * D + col);
-      const uint2 b = *reinterpret_cast<const uint2*>(z + r * D + col);
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
-      dyv[i][0] = bf16_lo(a.x); dyv[i][1] = bf16_hi(a.x); dyv[i][2] = bf16_lo(a.y); dyv[i][3] = bf16_hi(a.y);
-      xh[i][0] = (bf16_lo(b.x) - mu) * rs; xh[i][1] = (bf16_hi(b.x) - mu) * rs;
-      xh[i][2] = (bf16_lo(b.y) - mu) * rs; xh[i][3] = (bf16_hi(b.y) - mu) * rs;
-      const float gg[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        accg[i][j] += dyv[i][j] * xh[i][j];
-        accb[i][j] += dyv[i][j];
-        dyv[i][j] *= gg[j];  // dy * gamma
-        s1 += dyv[i][j];
-        s2 += dyv[i][j] * xh[i][j];
-      }
-    }
-    s1 = wsum(s1) / D;
-    s2 = wsum(s2) / D;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int col = (i * 32 + lane) * 4;
-      uint2 u;
-      u.x = pack_bf16x2(rs * (dyv[i][0] - s1 - xh[i][0] * s2), rs * (dyv[i][1] - s1 - xh[i][1] * s2));
-      u.y = pack_bf16x2(rs * (dyv[i][2] - s1 - xh[i][2] * s2), rs * (dyv[i][3] - s1 - xh[i][3] * s2));
-      *reinterpret_cast<uint2*>(dz + r * D + col) = u;
-    }
-  }
+layernorm_bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dz, long long rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float mu = mean[r], rs = rstd[r];
+  float dyg[VEC][4], xh[VEC][4];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int col = (i * 32 + lane) * 4;
+    const uint2 a = *reinterpret_cast<const uint2*>(dy + r * D + col);
+    const uint2 b = *reinterpret_cast<const uint2*>(z + r * D + col);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    dyg[i][0] = bf16_lo(a.x) * g.x; dyg[i][1] = bf16_hi(a.x) * g.y;
+    dyg[i][2] = bf16_lo(a.y) * g.z; dyg[i][3] = bf16_hi(a.y) * g.w;
+    xh[i][0] = (bf16_lo(b.x) - mu) * rs; xh[i][1] = (bf16_hi(b.x) - mu) * rs;
+    xh[i][2] = (bf16_lo(b.y) - mu) * rs; xh[i][3] = (bf16_hi(b.y) - mu) * rs;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&red[col + j], accg[i][j]);
-      atomicAdd(&red[D + col + j], accb[i][j]);
+      s1 += dyg[i][j];
+      s2 += dyg[i][j] * xh[i][j];
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    atomicAdd(dgamma + i, red[i]);
-    atomicAdd(dbeta + i, red[D + i]);
+  s1 = wsum(s1) / D;
+  s2 = wsum(s2) / D;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    uint2 u;
+    u.x = pack_bf16x2(rs * (dyg[i][0] - s1 - xh[i][0] * s2), rs * (dyg[i][1] - s1 - xh[i][1] * s2));
+    u.y = pack_bf16x2(rs * (dyg[i][2] - s1 - xh[i][2] * s2), rs * (dyg[i][3] - s1 - xh[i][3] * s2));
+    *reinterpret_cast<uint2*>(dz + r * D + col) = u;
   }
 }
 
-// ---- out[n] += sum_m x[m, n]   (x bf16 or f32 [rows, N], out f32).  grid = (N / 256 column slabs, row chunks)
+// (2) dgamma[n] += sum_m dy*xhat, dbeta[n] += sum_m dy.  Each thread owns 8 adjacent columns (128-bit loads) and
+// walks a chunk of rows; one f32 atomic per column per CTA.  grid = (ceil(D/8/128), row chunks).
+__global__ void __launch_bounds__(128)
+layernorm_bwd_affine_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                            float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int D,
+                            int rows_per_cta) {
+  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (col >= D) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  float ag[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = 0.f;
+#pragma unroll 4
+  for (long long r = r0; r < r1; ++r) {
+    const uint4 a = *reinterpret_cast<const uint4*>(dy + r * D + col);
+    const uint4 b = *reinterpret_cast<const uint4*>(z + r * D + col);
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    const float d[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y),
+                        bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
+    const float x[8] = {bf16_lo(b.x), bf16_hi(b.x), bf16_lo(b.y), bf16_hi(b.y),
+                        bf16_lo(b.z), bf16_hi(b.z), bf16_lo(b.w), bf16_hi(b.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ag[j] += d[j] * (x[j] - mu) * rs;
+      ab[j] += d[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(dgamma + col + j, ag[j]);
+    atomicAdd(dbeta + col + j, ab[j]);
+  }
+}
+
+// ---- out[n] += sum_m x[m, n]   (x bf16 or f32 [rows, N], out f32): 8 (bf16) / 4 (f32) columns per thread,
+// 128-bit loads, one atomic per column per CTA.  grid = (column slabs, row chunks)
 template <bool F32>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 colsum_kernel(const void* __restrict__ x, float* __restrict__ out, long long rows, int N, long long ld,
               int rows_per_cta) {
-  const int col = blockIdx.x * 256 + threadIdx.x;
+  constexpr int kPer = F32 ? 4 : 8;
+  const int col = (blockIdx.x * 128 + threadIdx.x) * kPer;
   if (col >= N) return;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = min(rows, r0 + rows_per_cta);
-  float acc = 0.f;
+  float acc[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) acc[j] = 0.f;
+#pragma unroll 4
   for (long long r = r0; r < r1; ++r) {
-    if constexpr (F32) acc += reinterpret_cast<const float*>(x)[r * ld + col];
-    else acc += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[r * ld + col]);
+    if constexpr (F32) {
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + r * ld + col);
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    } else {
+      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + r * ld + col);
+      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
   }
-  atomicAdd(out + col, acc);
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) atomicAdd(out + col + j, acc[j]);
 }
 
 // ---- f32 -> bf16 cast, 8 elements per thread
@@ -243,25 +259,31 @@ extern "C" int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const f
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(dy_bf16 && z_bf16 && mean && rstd && gamma && dz_bf16 && dgamma && dbeta, "null pointer");
   VQ_CHECK_ARG(rows > 0 && D % 128 == 0, "geometry");
-  const int rows_per_cta = 16;
-  const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
-  const size_t smem = 2 * (size_t)D * sizeof(float);
   const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(z_bf16);
   __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(dz_bf16);
-  LaunchScope scope(kKindRow, "layernorm_bwd", (int)rows, D, 0, 0, (double)rows * D * 6.0, stream);
-#define VQ_LNB_CASE(V)                                                                                         \
-  case V:                                                                                                      \
-    layernorm_bwd_kernel<V><<<grid, 256, smem, stream>>>(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, rows, D, \
-                                                         rows_per_cta);                                        \
+  {
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    LaunchScope scope(kKindRow, "layernorm_bwd_dz", (int)rows, D, 0, 0, (double)rows * D * 6.0, stream);
+#define VQ_LNB_CASE(V)                                                                                  \
+  case V:                                                                                               \
+    layernorm_bwd_dz_kernel<V><<<grid, 256, 0, stream>>>(dy, z, mean, rstd, gamma, dz, rows, D);        \
     break;
-  switch (D / 128) {
-    VQ_LNB_CASE(1) VQ_LNB_CASE(2) VQ_LNB_CASE(4) VQ_LNB_CASE(8) VQ_LNB_CASE(16) VQ_LNB_CASE(32)
-    default:
-      set_error("layernorm_bwd: unsupported width");
-      return VQ_ERR_UNSUPPORTED;
-  }
+    switch (D / 128) {
+      VQ_LNB_CASE(1) VQ_LNB_CASE(2) VQ_LNB_CASE(4) VQ_LNB_CASE(8) VQ_LNB_CASE(16) VQ_LNB_CASE(32)
+      default:
+        set_error("layernorm_bwd: unsupported width");
+        return VQ_ERR_UNSUPPORTED;
+    }
 #undef VQ_LNB_CASE
+  }
+  VQ_CHECK_CUDA(cudaGetLastError());
+  {
+    const int rows_per_cta = 32;
+    dim3 grid((D / 8 + 127) / 128, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
+    LaunchScope scope(kKindRow, "layernorm_bwd_affine", (int)rows, D, 0, 0, (double)rows * D * 4.0, stream);
+    layernorm_bwd_affine_kernel<<<grid, 128, 0, stream>>>(dy, z, mean, rstd, dgamma, dbeta, rows, D, rows_per_cta);
+  }
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
 }
@@ -270,11 +292,13 @@ extern "C" int vq_colsum(const void* x, int32_t dtype, float* out, int64_t rows,
                          vq_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(x && out && rows > 0 && N > 0 && ld >= N, "colsum arguments");
-  const int rows_per_cta = 64;
-  dim3 grid((N + 255) / 256, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
+  VQ_CHECK_ARG(N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0, "colsum: 16-byte rows");
+  const int rows_per_cta = 32;
+  const int per = dtype == VQ_F32 ? 4 : 8;
+  dim3 grid((N / per + 127) / 128, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
   LaunchScope scope(kKindRow, "colsum", (int)rows, N, 0, 0, (double)rows * N * (dtype == VQ_F32 ? 4.0 : 2.0), stream);
-  if (dtype == VQ_F32) colsum_kernel<true><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
-  else colsum_kernel<false><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
+  if (dtype == VQ_F32) colsum_kernel<true><<<grid, 128, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
+  else colsum_kernel<false><<<grid, 128, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
 }
