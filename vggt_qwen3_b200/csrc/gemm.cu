@@ -8,6 +8,8 @@
 // Both operands may be K-major or MN-major (UMMA descriptor + instruction-descriptor major bits), so the
 // same kernel serves forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without materialised transposes.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -48,11 +50,13 @@ struct GemmArgs {
   const float* pos_embed;
 };
 
-template <int BLOCK_N>
+// CG = CTAs per MMA (cta_group): 1 = one CTA owns a 128 x BLOCK_N tile; 2 = a CTA pair owns a 256 x BLOCK_N tile,
+// each CTA loading its 128 rows of A and BLOCK_N/2 rows of B.
+template <int BLOCK_N, int CG>
 struct GemmCfg {
-  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBTileBytes = (BLOCK_N / CG) * kBlockK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = (kStageBytes == 49152) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 / 512)
   // per-warp [bias|gamma] vectors (8 warps x BLOCK_N floats), q/k-norm affine (4 x 64), rope cos/sin tables
   static constexpr int kEpiVecBytes = 8 * BLOCK_N * 4 + 4 * 64 * 4 + 2 * kRopeSmemPos * 16 * 4;
@@ -100,12 +104,16 @@ __device__ __forceinline__ void load8(const void* base, long long off, float* v)
 }
 
 // MODE: VQ_EPI_* ; OUT_F32: C/add dtype
-template <int BLOCK_N, int MODE, bool OUT_F32>
+template <int BLOCK_N, int MODE, bool OUT_F32, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmArgs g) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CG>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kTileM = kBlockM * CG;                       // rows of C per (pair-)tile
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;  // 0 = leader (issues the MMAs)
+  const int first_tile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -137,13 +145,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 256);
+      mbar_init(bar_tempty + 8 * s, 256 * CG);  // every epilogue thread of the (pair of) CTA(s)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   if constexpr (MODE == VQ_EPI_QKV_ROPE) {
     if (g.apply_qknorm_rope) {
@@ -161,6 +174,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -172,7 +186,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+        if constexpr (CG == 2) tma_load_2d_pair(dst, map, bar, c0, c1);
+        else tma_load_2d(dst, map, bar, c0, c1);
+      };
+      constexpr int kBRows = BLOCK_N / CG;  // rows (N indices) of B this CTA loads
+      for (int tile = first_tile; tile < g.total_tiles; tile += tile_stride) {
         const int z = tile / tiles_per_z;
         const int rem = tile - z * tiles_per_z;
         const int m_blk = rem / g.n_tiles;
@@ -180,27 +199,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int z0 = z / g.Z1, z1 = z - z0 * g.Z1;
         const int a_r = z0 * g.a_r0 + z1 * g.a_r1, a_c = z0 * g.a_c0 + z1 * g.a_c1;
         const int b_r = z0 * g.b_r0 + z1 * g.b_r1, b_c = z0 * g.b_c0 + z1 * g.b_c1;
+        const int m0 = m_blk * kTileM + (int)cta_rank * kBlockM;       // first A row of this CTA
+        const int n0 = n_blk * BLOCK_N + (int)cta_rank * kBRows;       // first B row of this CTA
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;
-          mbar_arrive_expect_tx(full, Cfg::kStageBytes);
+          // the leader's barrier collects the bytes of both CTAs
+          if (cta_rank == 0) mbar_arrive_expect_tx(full, Cfg::kStageBytes * CG);
           const uint32_t sa = smem_a + stage * kATileBytes;
           const uint32_t sb = smem_b + stage * Cfg::kBTileBytes;
           if (!g.a_mn) {
-            tma_load_2d(sa, &tmA, full, a_c + kb * kBlockK, a_r + m_blk * kBlockM);
+            load(sa, &tmA, full, a_c + kb * kBlockK, a_r + m0);
           } else {
 #pragma unroll
             for (int i = 0; i < kBlockM / 64; ++i)
-              tma_load_2d(sa + i * (kBlockK * 128), &tmA, full, a_c + m_blk * kBlockM + i * 64,
-                          a_r + kb * kBlockK);
+              load(sa + i * (kBlockK * 128), &tmA, full, a_c + m0 + i * 64, a_r + kb * kBlockK);
           }
           if (!g.b_mn) {
-            tma_load_2d(sb, &tmB, full, b_c + kb * kBlockK, b_r + n_blk * BLOCK_N);
+            load(sb, &tmB, full, b_c + kb * kBlockK, b_r + n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_N / 64; ++i)
-              tma_load_2d(sb + i * (kBlockK * 128), &tmB, full, b_c + n_blk * BLOCK_N + i * 64,
-                          b_r + kb * kBlockK);
+            for (int i = 0; i < kBRows / 64; ++i)
+              load(sb + i * (kBlockK * 128), &tmB, full, b_c + n0 + i * 64, b_r + kb * kBlockK);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -208,8 +228,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, g.a_mn, g.b_mn);
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, g.a_mn, g.b_mn);
       // K-major: 8-row groups 1024 B apart, k-step = 32 B inside the 128 B swizzle row.
       // MN-major: 8-k groups 1024 B apart, 64-wide M/N chunks kBlockK*128 B apart, k-step = 16 rows.
       const uint32_t a_lbo = g.a_mn ? kBlockK * 128 : 16, b_lbo = g.b_mn ? kBlockK * 128 : 16;
@@ -218,7 +238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < g.total_tiles; tile += tile_stride, ++it) {
         const int as = it & 1;
         const uint32_t as_phase = (it >> 1) & 1;
         mbar_wait(bar_tempty + 8 * as, as_phase ^ 1);
@@ -233,12 +253,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+            if constexpr (CG == 2) umma_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+            else umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CG == 2) umma_commit_pair(bar_empty + 8 * stage);
+          else umma_commit(bar_empty + 8 * stage);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * as);  // accumulator complete
+        // accumulator complete (published to both CTAs of a pair)
+        if constexpr (CG == 2) umma_commit_pair(bar_tfull + 8 * as);
+        else umma_commit(bar_tfull + 8 * as);
       }
     }
   } else {
@@ -253,7 +278,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int row_in_tile = quarter * 32 + lane;
     float* my_vec = epi_vec + (warp - 2) * (2 * kHalfN);  // [bias | gamma] x kHalfN, private to this warp
     int it = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < g.total_tiles; tile += tile_stride, ++it) {
       const int z = tile / tiles_per_z;
       const int rem = tile - z * tiles_per_z;
       const int m_blk = rem / g.n_tiles;
@@ -280,28 +305,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(bar_tfull + 8 * as, as_phase);
       tc_fence_after();
 
-      const int m = m_blk * kBlockM + row_in_tile;
+      const int m = m_blk * kTileM + (int)cta_rank * kBlockM + row_in_tile;
       const bool row_ok = m < g.M;
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N + half * kHalfN;
 
       if constexpr (MODE == VQ_EPI_QKV_ROPE) {
         // One head (64 columns) at a time; the whole head row lives in this thread's registers.
-        static_assert(kHalfN == 64, "QKV epilogue: one head per warp per tile");
+        static_assert(kHalfN % 64 == 0, "QKV epilogue: whole heads per warp");
         const int D3 = g.N / 3;  // q | k | v column blocks
-        if (n_base < g.N) {
+#pragma unroll 1
+        for (int hh = 0; hh < kHalfN / 64; ++hh) {
+          const int n_head = n_base + hh * 64;
+          if (n_head >= g.N) break;
           float v[64];
           {
             uint32_t r[32];
-            tmem_ld32(taddr, r);
+            tmem_ld32(taddr + hh * 64, r);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + my_vec[i];
-            tmem_ld32(taddr + 32, r);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + my_vec[hh * 64 + i];
+            tmem_ld32(taddr + hh * 64 + 32, r);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]) + my_vec[32 + i];
+            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]) + my_vec[hh * 64 + 32 + i];
           }
-          const int which = n_base / D3;  // 0 = q, 1 = k, 2 = v
+          const int which = n_head / D3;  // 0 = q, 1 = k, 2 = v
           if (which < 2 && g.apply_qknorm_rope) {
             const float* w = qk_vec + which * 128;  // [w | b] of q_norm or k_norm
             float mean = 0.f;
@@ -357,7 +385,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int i = 0; i < 64; ++i) v[i] *= g.q_scale;
           }
           if (row_ok) {
-            const long long off = (c_r + m) * g.ldc + c_c + n_base;
+            const long long off = (c_r + m) * g.ldc + c_c + n_head;
 #pragma unroll
             for (int i = 0; i < 64; i += 8) store8<OUT_F32>(g.C, off + i, v + i);
           }
@@ -435,43 +463,68 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
-      // release the accumulator stage back to the MMA warp
+      // release the accumulator stage back to the (leader's) MMA warp
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * as);
+      if constexpr (CG == 2) mbar_arrive_leader(bar_tempty + 8 * as);
+      else mbar_arrive(bar_tempty + 8 * as);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still uses it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BLOCK_N, int MODE, bool OUT_F32>
-static int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g,
-                       cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  auto kern = gemm_kernel<BLOCK_N, MODE, OUT_F32>;
+template <int BLOCK_N, int MODE, bool OUT_F32, int CG>
+static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, CG>;
+  auto kern = gemm_kernel<BLOCK_N, MODE, OUT_F32, CG>;
   static bool configured = false;
   if (!configured) {
-    VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
+    VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  int grid = g.total_tiles < num_sms() ? g.total_tiles : num_sms();
-  {
-    static const char* const kTags[] = {"gemm_linear", "gemm_gelu", "gemm_gelu_bwd", "gemm_qkv_rope", "gemm_patch"};
-    const double Z = (double)g.total_tiles / ((double)g.m_tiles * g.n_tiles);
-    const double mnk = (double)g.M * g.N * g.K;
-    const double bytes = Z * (2.0 * ((double)g.M * g.K + (double)g.N * g.K) +
-                              (OUT_F32 ? 4.0 : 2.0) * (double)g.M * g.N * (g.add ? 2.0 : 1.0));
-    LaunchScope scope(kKindGemm, kTags[MODE], g.M, g.N, g.K, 2.0 * mnk * Z, bytes, stream);
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*tmA, *tmB, g);
+  const int sms = num_sms();
+  int grid;
+  if (CG == 2) {
+    const int pairs = sms / 2;
+    grid = 2 * (g.total_tiles < pairs ? g.total_tiles : pairs);
+  } else {
+    grid = g.total_tiles < sms ? g.total_tiles : sms;
   }
-  VQ_CHECK_CUDA(cudaGetLastError());
+  static const char* const kTags[] = {"gemm_linear", "gemm_gelu", "gemm_gelu_bwd", "gemm_qkv_rope", "gemm_patch"};
+  const double Z = (double)g.total_tiles / ((double)g.m_tiles * g.n_tiles);
+  const double mnk = (double)g.M * g.N * g.K;
+  const double bytes = Z * (2.0 * ((double)g.M * g.K + (double)g.N * g.K) +
+                            (OUT_F32 ? 4.0 : 2.0) * (double)g.M * g.N * (g.add ? 2.0 : 1.0));
+  LaunchScope scope(kKindGemm, kTags[MODE], g.M, g.N, g.K, 2.0 * mnk * Z, bytes, stream);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VQ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *tmA, *tmB, g));
   return VQ_OK;
+}
+
+template <int BLOCK_N, int MODE, bool OUT_F32>
+static int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g, cudaStream_t stream,
+                       int cta_group) {
+  if (cta_group == 2) return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 2>(tmA, tmB, g, stream);
+  return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 1>(tmA, tmB, g, stream);
 }
 
 static inline bool fits_i32(long long v) { return v >= INT32_MIN && v <= INT32_MAX; }
@@ -500,14 +553,22 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
   VQ_CHECK_ARG(!d->bias || (reinterpret_cast<uintptr_t>(d->bias) % 16) == 0, "bias alignment");
   VQ_CHECK_ARG(!d->gamma || (reinterpret_cast<uintptr_t>(d->gamma) % 16) == 0, "gamma alignment");
 
-  // Tile width: 256 when the problem fills the machine with wide tiles, else 128.
-  const int m_tiles = (d->M + kBlockM - 1) / kBlockM;
+  // Tiling.  Large unbatched problems run on CTA pairs (cta_group::2, 256 x 256 tiles: each CTA stages only half
+  // of B, which keeps smem traffic within the 128 B/clk port at full tensor rate); batched / small-M problems
+  // use single CTAs with 128 x 256 or 128 x 128 tiles.
+  static const int force_cg = [] {
+    const char* e = getenv("VQ_GEMM_CTA_GROUP");
+    return e ? atoi(e) : 0;
+  }();
+  int cg = (Z0 * Z1 == 1 && d->M > kBlockM && d->N >= 256) ? 2 : 1;
+  if (force_cg == 1 || force_cg == 2) cg = (force_cg == 2 && (Z0 * Z1 != 1 || d->N < 256)) ? 1 : force_cg;
+  const int m_tiles = (d->M + kBlockM * cg - 1) / (kBlockM * cg);
   int block_n = 256;
-  {
+  if (cg == 1) {
     const long long tiles256 = (long long)m_tiles * ((d->N + 255) / 256) * Z0 * Z1;
     const int sms = num_sms() > 0 ? num_sms() : 148;
     if (d->N % 256 != 0 || tiles256 < 4LL * sms) block_n = 128;
-    if (d->epilogue == VQ_EPI_QKV_ROPE) block_n = 128;  // register budget of the per-head epilogue
+    if (d->epilogue == VQ_EPI_QKV_ROPE && d->N % 256 != 0) block_n = 128;
   }
   const int n_tiles = (d->N + block_n - 1) / block_n;
 
@@ -530,7 +591,7 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
       get_tmap_2d_bf16(d->A, a_cols, a_rows, d->lda, 64, d->a_major ? kBlockK : kBlockM);
   if (!tmA) return VQ_ERR_CUDA;
   const CUtensorMap* tmB =
-      get_tmap_2d_bf16(d->B, b_cols, b_rows, d->ldb, 64, d->b_major ? kBlockK : block_n);
+      get_tmap_2d_bf16(d->B, b_cols, b_rows, d->ldb, 64, d->b_major ? kBlockK : block_n / cg);
   if (!tmB) return VQ_ERR_CUDA;
 
   GemmArgs g;
@@ -567,20 +628,20 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
   switch (d->epilogue) {
     case VQ_EPI_LINEAR:
       if (block_n == 256)
-        return f32 ? launch_gemm<256, VQ_EPI_LINEAR, true>(tmA, tmB, g, stream)
-                   : launch_gemm<256, VQ_EPI_LINEAR, false>(tmA, tmB, g, stream);
-      return f32 ? launch_gemm<128, VQ_EPI_LINEAR, true>(tmA, tmB, g, stream)
-                 : launch_gemm<128, VQ_EPI_LINEAR, false>(tmA, tmB, g, stream);
+        return f32 ? launch_gemm<256, VQ_EPI_LINEAR, true>(tmA, tmB, g, stream, cg)
+                   : launch_gemm<256, VQ_EPI_LINEAR, false>(tmA, tmB, g, stream, cg);
+      return f32 ? launch_gemm<128, VQ_EPI_LINEAR, true>(tmA, tmB, g, stream, cg)
+                 : launch_gemm<128, VQ_EPI_LINEAR, false>(tmA, tmB, g, stream, cg);
     case VQ_EPI_GELU:
       VQ_CHECK_ARG(!f32, "GELU epilogue writes bf16");
       VQ_CHECK_ARG(d->bias != nullptr, "GELU epilogue needs a bias");
-      return block_n == 256 ? launch_gemm<256, VQ_EPI_GELU, false>(tmA, tmB, g, stream)
-                            : launch_gemm<128, VQ_EPI_GELU, false>(tmA, tmB, g, stream);
+      return block_n == 256 ? launch_gemm<256, VQ_EPI_GELU, false>(tmA, tmB, g, stream, cg)
+                            : launch_gemm<128, VQ_EPI_GELU, false>(tmA, tmB, g, stream, cg);
     case VQ_EPI_GELU_BWD:
       VQ_CHECK_ARG(!f32, "GELU_BWD epilogue writes bf16");
       VQ_CHECK_ARG(d->aux != nullptr, "GELU_BWD epilogue needs aux (saved pre-activation)");
-      return block_n == 256 ? launch_gemm<256, VQ_EPI_GELU_BWD, false>(tmA, tmB, g, stream)
-                            : launch_gemm<128, VQ_EPI_GELU_BWD, false>(tmA, tmB, g, stream);
+      return block_n == 256 ? launch_gemm<256, VQ_EPI_GELU_BWD, false>(tmA, tmB, g, stream, cg)
+                            : launch_gemm<128, VQ_EPI_GELU_BWD, false>(tmA, tmB, g, stream, cg);
     case VQ_EPI_QKV_ROPE:
       VQ_CHECK_ARG(!f32, "QKV epilogue writes bf16");
       VQ_CHECK_ARG(d->bias != nullptr, "QKV epilogue needs a bias");
@@ -589,13 +650,14 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
       VQ_CHECK_ARG(!d->apply_qknorm_rope || (d->qn_w && d->qn_b && d->kn_w && d->kn_b &&
                                              d->rope_cos && d->rope_sin),
                    "QKV epilogue: q/k norm and rope tables required");
-      return launch_gemm<128, VQ_EPI_QKV_ROPE, false>(tmA, tmB, g, stream);
+      return block_n == 256 ? launch_gemm<256, VQ_EPI_QKV_ROPE, false>(tmA, tmB, g, stream, cg)
+                            : launch_gemm<128, VQ_EPI_QKV_ROPE, false>(tmA, tmB, g, stream, cg);
     case VQ_EPI_PATCH:
       VQ_CHECK_ARG(f32, "PATCH epilogue writes the f32 token stream");
       VQ_CHECK_ARG(d->pos_embed && d->n_patches > 0 && d->tokens_per_frame > 0, "PATCH epilogue args");
       VQ_CHECK_ARG(Z0 * Z1 == 1, "PATCH epilogue is not batched");
-      return block_n == 256 ? launch_gemm<256, VQ_EPI_PATCH, true>(tmA, tmB, g, stream)
-                            : launch_gemm<128, VQ_EPI_PATCH, true>(tmA, tmB, g, stream);
+      return block_n == 256 ? launch_gemm<256, VQ_EPI_PATCH, true>(tmA, tmB, g, stream, cg)
+                            : launch_gemm<128, VQ_EPI_PATCH, true>(tmA, tmB, g, stream, cg);
     default:
       set_error("unknown epilogue");
       return VQ_ERR_INVALID;
