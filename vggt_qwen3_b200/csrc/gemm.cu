@@ -1,9 +1,9 @@
 // vq_gemm: persistent, warp-specialised bf16 GEMM on the 5th-gen tensor cores (sm_100a).
 //
-//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B boxes) -> smem ring, mbarrier full/empty
-//   warp 1      MMA issuer     one lane issues tcgen05.mma (128 x BLOCK_N x 16) into a double-buffered
+//   warps 0..7  epilogue       tcgen05.ld (one accumulator row per thread) -> fused epilogue -> global
+//   warp 8      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B boxes) -> smem ring, mbarrier full/empty
+//   warp 9      MMA issuer     one elected lane issues tcgen05.mma (128/256 x BLOCK_N x 16) into a double-buffered
 //                              TMEM accumulator; tcgen05.commit releases smem stages / publishes tiles
-//   warps 2..5  epilogue       tcgen05.ld (one accumulator row per thread) -> fused epilogue -> global
 //
 // Both operands may be K-major or MN-major (UMMA descriptor + instruction-descriptor major bits), so the
 // same kernel serves forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without materialised transposes.
@@ -19,7 +19,9 @@ namespace vq {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 320;     // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kGemmThreads = 320;     // 8 epilogue warps (0..7) + TMA warp (8) + MMA warp (9)
+constexpr int kTmaWarp = 8;
+constexpr int kMmaWarp = 9;
 constexpr int kRopeSmemPos = 64;       // rope table positions staged in smem (larger tables are read from global)
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 
@@ -136,7 +138,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) {
@@ -145,11 +147,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 256 * CG);  // every epilogue thread of the (pair of) CTA(s)
+      mbar_init(bar_tempty + 8 * s, 8 * CG);  // one elected lane per epilogue warp of the (pair of) CTA(s)
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     if constexpr (CG == 2) {
       tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
       tmem_relinquish_pair();
@@ -181,7 +183,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_kb = (g.K + kBlockK - 1) / kBlockK;
   const int tiles_per_z = g.m_tiles * g.n_tiles;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -226,15 +228,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && cta_rank == 0) {
+    // The whole warp runs the control flow so that waits and descriptor arithmetic stay warp-uniform; only the
+    // tcgen05 instructions are predicated on one elected lane.  (Highest warp id: favoured by the scheduler.)
+    if (cta_rank == 0) {
       const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, g.a_mn, g.b_mn);
       // K-major: 8-row groups 1024 B apart, k-step = 32 B inside the 128 B swizzle row.
       // MN-major: 8-k groups 1024 B apart, 64-wide M/N chunks kBlockK*128 B apart, k-step = 16 rows.
       const uint32_t a_lbo = g.a_mn ? kBlockK * 128 : 16, b_lbo = g.b_mn ? kBlockK * 128 : 16;
-      const uint32_t a_kstep = g.a_mn ? (kUmmaK * 128) : (kUmmaK * 2);
-      const uint32_t b_kstep = g.b_mn ? (kUmmaK * 128) : (kUmmaK * 2);
+      // descriptor start-address field is in 16-byte units
+      const uint32_t a_kstep = (g.a_mn ? (kUmmaK * 128) : (kUmmaK * 2)) >> 4;
+      const uint32_t b_kstep = (g.b_mn ? (kUmmaK * 128) : (kUmmaK * 2)) >> 4;
+      const uint64_t desc_a0 = make_smem_desc(smem_a, a_lbo, 1024);
+      const uint64_t desc_b0 = make_smem_desc(smem_b, b_lbo, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -245,38 +252,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
+          mbar_wait_fast(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_a + stage * kATileBytes;
-          const uint32_t sb = smem_b + stage * Cfg::kBTileBytes;
+          const uint64_t desc_a = desc_a0 + (uint64_t)(stage * (kATileBytes >> 4));
+          const uint64_t desc_b = desc_b0 + (uint64_t)(stage * (Cfg::kBTileBytes >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            if constexpr (CG == 2) umma_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
-            else umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t adesc = desc_a + (uint64_t)(k * a_kstep);
+              const uint64_t bdesc = desc_b + (uint64_t)(k * b_kstep);
+              if constexpr (CG == 2) umma_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+              else umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+            }
+            // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+            if constexpr (CG == 2) umma_commit_pair(bar_empty + 8 * stage);
+            else umma_commit(bar_empty + 8 * stage);
           }
-          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
-          if constexpr (CG == 2) umma_commit_pair(bar_empty + 8 * stage);
-          else umma_commit(bar_empty + 8 * stage);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         // accumulator complete (published to both CTAs of a pair)
-        if constexpr (CG == 2) umma_commit_pair(bar_tfull + 8 * as);
-        else umma_commit(bar_tfull + 8 * as);
+        if (elect_one()) {
+          if constexpr (CG == 2) umma_commit_pair(bar_tfull + 8 * as);
+          else umma_commit(bar_tfull + 8 * as);
+        }
+        __syncwarp();
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 0..7) =====================
     // Two warps share each TMEM lane quarter (hardware: warp w may touch lanes 32*(w%4)..+31) and split the
     // tile's columns in halves; one accumulator row per thread.  Per-column vectors (bias, LayerScale gamma)
     // are staged per warp in smem before the accumulator is waited for, TMEM loads are double-buffered and all
     // global loads of a 32-column chunk are issued before its math, so no latency sits on the critical path.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = warp >> 2;
     constexpr int kHalfN = BLOCK_N / 2;
     const int row_in_tile = quarter * 32 + lane;
-    float* my_vec = epi_vec + (warp - 2) * (2 * kHalfN);  // [bias | gamma] x kHalfN, private to this warp
+    float* my_vec = epi_vec + warp * (2 * kHalfN);  // [bias | gamma] x kHalfN, private to this warp
     int it = 0;
     for (int tile = first_tile; tile < g.total_tiles; tile += tile_stride, ++it) {
       const int z = tile / tiles_per_z;
@@ -465,15 +478,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       // release the accumulator stage back to the (leader's) MMA warp
       tc_fence_before();
-      if constexpr (CG == 2) mbar_arrive_leader(bar_tempty + 8 * as);
-      else mbar_arrive(bar_tempty + 8 * as);
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_leader(bar_tempty + 8 * as);
+        else mbar_arrive(bar_tempty + 8 * as);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still uses it
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
     else tmem_dealloc(tmem_base, Cfg::kTmemCols);

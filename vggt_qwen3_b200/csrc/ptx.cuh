@@ -48,6 +48,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// True in exactly one (elected) lane of a fully converged warp.  Used to predicate only the tcgen05 / TMA issue
+// instructions, so that the surrounding address arithmetic stays warp-uniform (uniform datapath, no R2UR).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Lean wait for hot loops (no hang guard).
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if VQ_HANG_GUARD
   uint32_t spins = 0;
@@ -296,6 +314,9 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
