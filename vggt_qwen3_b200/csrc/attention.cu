@@ -266,6 +266,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
         if (tlane) VQ_TRACE(trole, j, 4);
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t p[64];
+        // One warp alone reaches only ~70 % of the MUFU rate, two together saturate it: the token is handed over
+        // after kHandoff of the 64 pair-iterations so the other warpgroup's exponentials overlap the tail of ours.
+        constexpr int kHandoff = 40;
 #pragma unroll
         for (int i = 0; i < 64; i += 2) {
           float p0, p1, p2, p3;
@@ -283,12 +286,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
           sum4[3] += p3;
           p[i] = pack_bf16x2(p0, p1);
           p[i + 1] = pack_bf16x2(p2, p3);
-        }
-        if (pingpong) {
-          // hand the token over once this warp's exponentials have been issued
-          asm volatile("" ::"f"(sum4[0]), "f"(sum4[1]), "f"(sum4[2]), "f"(sum4[3]));
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_token + 8 * (t ^ 1));
+          if (i + 2 == kHandoff && pingpong) {
+            asm volatile("" ::"f"(sum4[0]), "f"(sum4[1]), "f"(sum4[2]), "f"(sum4[3]));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_token + 8 * (t ^ 1));
+          }
         }
         if (tlane) VQ_TRACE(trole, j, 5);
         const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
