@@ -52,9 +52,10 @@ class _MockVGGT(nn.Module):
 
 
 class VGGTQwen3VLM(nn.Module):
-    def __init__(self, config: VisionLanguageConfig, text_model: Optional[nn.Module] = None, tokenizer=None) -> None:
-        """`text_model` / `tokenizer` may be injected (tests, offline boxes); otherwise they are loaded from the
-        hub exactly as the reference does (:31-42)."""
+    def __init__(self, config: VisionLanguageConfig, text_model: Optional[nn.Module] = None, tokenizer=None,
+                 vision_model: Optional[nn.Module] = None) -> None:
+        """`text_model` / `tokenizer` / `vision_model` may be injected (tests, offline boxes); otherwise they are
+        loaded exactly as the reference does (:31-42, :60-111)."""
         super().__init__()
         dtype = getattr(torch, config.dtype, torch.bfloat16) if isinstance(config.dtype, str) else torch.bfloat16
         if tokenizer is None or text_model is None:
@@ -71,7 +72,8 @@ class VGGTQwen3VLM(nn.Module):
                     text_model.resize_token_embeddings(len(tokenizer))
         self.tokenizer = tokenizer
         self.text_model = text_model
-        self.vision_model = self._load_vggt(config.vision_ckpt_dir, config.num_vis_tokens)
+        self.vision_model = vision_model if vision_model is not None else self._load_vggt(
+            config.vision_ckpt_dir, config.num_vis_tokens)
         for p in self.vision_model.parameters():
             p.requires_grad_(not config.freeze_vision)
         hidden = self.text_model.config.hidden_size
@@ -125,19 +127,15 @@ class VGGTQwen3VLM(nn.Module):
         return self.projector(agg.to(dtype=self.projector.in_proj.weight.dtype))
 
     def encode_geom(self, geom_token: Optional[Dict[str, torch.Tensor]]) -> Optional[torch.Tensor]:
+        """[B, geom_tokens, hidden] from per-view (R 9 | t 3 | K 9 | depth_hist 16) features averaged over views
+        (reference :164-177); None when there is no geometry input or geom_tokens == 0."""
         if not geom_token or self.geom_tokens == 0:
             return None
-        feats = torch.cat(
-            [
-                geom_token.get("R", torch.zeros_like(geom_token["t"])),
-                geom_token.get("t", torch.zeros_like(geom_token["R"])),
-                geom_token.get("K", torch.zeros_like(geom_token["R"])),
-                geom_token.get("depth_hist", torch.zeros_like(geom_token["R"])),
-            ],
-            dim=-1,
-        )
-        geom = self.geom_head(feats.mean(dim=1))
-        return geom.unsqueeze(1).expand(-1, self.geom_tokens, -1)
+        parts = []
+        for key, like in (("R", "t"), ("t", "R"), ("K", "R"), ("depth_hist", "R")):
+            parts.append(geom_token[key] if key in geom_token else torch.zeros_like(geom_token[like]))
+        pooled = torch.cat(parts, dim=-1).mean(dim=1)
+        return self.geom_head(pooled).unsqueeze(1).expand(-1, self.geom_tokens, -1)
 
     def build_inputs_embeds(self, images: torch.Tensor, geom_token, input_ids: torch.Tensor,
                             trainable_projector: bool = False) -> torch.Tensor:
