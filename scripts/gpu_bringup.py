@@ -164,6 +164,11 @@ CASES = {
     "gemm_t_fc2": lambda: case_gemm(10992, 1024, 4096, epi="lsres", out_f32=True, timing=True),
     "gemm_t_proj": lambda: case_gemm(10992, 1024, 1024, epi="lsres", out_f32=True, timing=True),
     "gemm_t_8k": lambda: case_gemm(8192, 8192, 8192, timing=True),
+    # --- c3 (M = 32*1374)
+    "gemm_t3_qkv": lambda: case_gemm(43968, 3072, 1024, timing=True),
+    "gemm_t3_fc1": lambda: case_gemm(43968, 4096, 1024, epi="gelu", timing=True),
+    "gemm_t3_fc2": lambda: case_gemm(43968, 1024, 4096, epi="lsres", out_f32=True, timing=True),
+    "gemm_t3_proj": lambda: case_gemm(43968, 1024, 1024, epi="lsres", out_f32=True, timing=True),
     # --- attention
     "attn_128": lambda: case_attn(1, 128, 1),
     "attn_256": lambda: case_attn(1, 256, 2),
@@ -184,7 +189,7 @@ def main():
     for name in names:
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=180)
+            p = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=75)
             out = (p.stdout.strip().splitlines() or ["<no output>"])[-1]
             if p.returncode != 0:
                 n_fail += 1
@@ -194,6 +199,8 @@ def main():
             n_fail += 1
             out = f"TIMEOUT {name}"
         print(f"{out}  [{time.time()-t0:.1f}s]", flush=True)
+        if out.startswith("TIMEOUT"):
+            break  # a hung kernel: do not burn GPU time on the remaining cases
     print(f"bringup: {len(names)-n_fail}/{len(names)} passed", flush=True)
     sys.exit(1 if n_fail else 0)
 

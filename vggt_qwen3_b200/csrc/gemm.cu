@@ -19,7 +19,8 @@ namespace vq {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 320;     // 8 epilogue warps (0..7) + TMA warp (8) + MMA warp (9)
+constexpr int kGemmThreads = 384;     // 8 epilogue warps (0..7) + TMA warp (8) + MMA warp (9) + 2 idle warps: setmaxnreg
+                                      // is a warpgroup-wide instruction, so the third warpgroup is complete
 constexpr int kTmaWarp = 8;
 constexpr int kMmaWarp = 9;
 constexpr int kRopeSmemPos = 64;       // rope table positions staged in smem (larger tables are read from global)
@@ -54,50 +55,107 @@ struct GemmArgs {
 
 // CG = CTAs per MMA (cta_group): 1 = one CTA owns a 128 x BLOCK_N tile; 2 = a CTA pair owns a 256 x BLOCK_N tile,
 // each CTA loading its 128 rows of A and BLOCK_N/2 rows of B.
+constexpr int kStageLd = 36;                          // floats per staged row: 32 columns + 4 pad (conflict-free 128-bit rows)
+constexpr int kStageWarpFloats = 32 * kStageLd;       // one 32 x 32 fp32 transposition buffer per epilogue warp
+constexpr int kSmemLimit = 232448;                    // 227 KB per CTA
+
 template <int BLOCK_N, int CG>
 struct GemmCfg {
   static constexpr int kBTileBytes = (BLOCK_N / CG) * kBlockK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = (kStageBytes == 49152) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 / 512)
-  // per-warp [bias|gamma] vectors (8 warps x BLOCK_N floats), q/k-norm affine (4 x 64), rope cos/sin tables
-  static constexpr int kEpiVecBytes = 8 * BLOCK_N * 4 + 4 * 64 * 4 + 2 * kRopeSmemPos * 16 * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiVecBytes;
+  // per-warp [bias|gamma] vectors (8 warps x BLOCK_N floats), then EITHER the QKV extras (q/k-norm affine 4 x 64 and
+  // the rope cos/sin tables) OR the per-warp transposition buffers of the other epilogues
+  static constexpr int kQkvExtraBytes = 4 * 64 * 4 + 2 * kRopeSmemPos * 16 * 4;
+  static constexpr int kTransposeBytes = 8 * kStageWarpFloats * 4;
+  static constexpr int kEpiVecBytes =
+      8 * BLOCK_N * 4 + (kQkvExtraBytes > kTransposeBytes ? kQkvExtraBytes : kTransposeBytes);
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + 256 /*barriers*/ + kEpiVecBytes;
+  static constexpr int kStagesFit = (kSmemLimit - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
+  static_assert(kStages >= 3, "smem ring too shallow");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+// ---- GELU (exact erf form) without erff(): Phi(x) = 0.5 (1 + E(t)), t = clamp(x, -4.2, 4.2), E(t) = t P(t^2) with P a
+// degree-8 minimax polynomial constrained to E(4.2) = 1 (so gelu(x) = x for x >= 4.2 and 0 for x <= -4.2).
+// Max abs error of gelu against the erf definition: 5.9e-5 (bf16 rounding of the result is 2e-3 relative).
+// Evaluated two columns at a time with packed fp32 FMAs (FFMA2).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
 }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+__device__ __forceinline__ float clamp_sym(float x, float c) {  // sign(x) * min(|x|, c) in one FMNMX
+  float t;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(t) : "f"(x), "f"(c));
+  return t;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// E(t) = erf(t / sqrt(2)) for |t| <= 4.2, both lanes
+__device__ __forceinline__ float2 erf_sqrt2_poly2(float2 t) {
+  const float2 u = ffma2(t, t, splat2(0.f));
+  float2 p = splat2(9.847654636e-11f);
+  p = ffma2(p, u, splat2(-9.591337502e-09f));
+  p = ffma2(p, u, splat2(4.144957018e-07f));
+  p = ffma2(p, u, splat2(-1.057913687e-05f));
+  p = ffma2(p, u, splat2(1.796719589e-04f));
+  p = ffma2(p, u, splat2(-2.172918525e-03f));
+  p = ffma2(p, u, splat2(1.948188245e-02f));
+  p = ffma2(p, u, splat2(-1.324441582e-01f));
+  p = ffma2(p, u, splat2(7.976739407e-01f));
+  return ffma2(p, t, splat2(0.f));
+}
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  const float2 t = make_float2(clamp_sym(x.x, 4.2f), clamp_sym(x.y, 4.2f));
+  const float2 e = erf_sqrt2_poly2(t);
+  const float2 hx = ffma2(x, splat2(0.5f), splat2(0.f));
+  return ffma2(hx, e, hx);
+}
+// gelu'(x) = Phi(x) + x phi(x)
+__device__ __forceinline__ float2 gelu_grad2(float2 x) {
+  const float2 t = make_float2(clamp_sym(x.x, 4.2f), clamp_sym(x.y, 4.2f));
+  const float2 e = erf_sqrt2_poly2(t);
+  const float2 cdf = ffma2(e, splat2(0.5f), splat2(0.5f));
+  const float2 a = ffma2(x, x, splat2(0.f));
+  // phi(x) = exp(-x^2/2) / sqrt(2 pi) = 0.39894228 * 2^(-0.72134752 x^2)
+  const float2 pdf = make_float2(0.39894228040143268f * ex2_approx(-0.72134752044448170f * a.x),
+                                 0.39894228040143268f * ex2_approx(-0.72134752044448170f * a.y));
+  return ffma2(x, pdf, cdf);
 }
 
+// 8 consecutive elements (QKV epilogue: bf16 only)
+__device__ __forceinline__ void store8_bf16(void* base, long long off, const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = u;
+}
+// One 16-byte access: 4 f32 or 8 bf16 consecutive elements.
 template <bool F32>
-__device__ __forceinline__ void store8(void* base, long long off, const float* v) {
+__device__ __forceinline__ void storev(void* base, long long off, const float* v) {
   if constexpr (F32) {
-    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
-    p[0] = make_float4(v[0], v[1], v[2], v[3]);
-    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
-    uint4 u;
-    u.x = pack_bf16x2(v[0], v[1]);
-    u.y = pack_bf16x2(v[2], v[3]);
-    u.z = pack_bf16x2(v[4], v[5]);
-    u.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = u;
+    store8_bf16(base, off, v);
   }
 }
 template <bool F32>
-__device__ __forceinline__ void load8(const void* base, long long off, float* v) {
+__device__ __forceinline__ void loadv(const void* base, long long off, float* v) {
   if constexpr (F32) {
-    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
-    float4 a = p[0], b = p[1];
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
-    uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
     v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x);
     v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
     v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z);
@@ -133,6 +191,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* epi_vec = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
   float* qk_vec = epi_vec + 8 * BLOCK_N;        // [q_w | q_b | k_w | k_b] x 64
   float* rope_vec = qk_vec + 4 * 64;            // [cos | sin] x kRopeSmemPos x 16
+  float* stage_vec = epi_vec + 8 * BLOCK_N;     // aliases the QKV extras: 8 x [32][kStageLd] f32 transposition buffers
   const bool rope_in_smem = g.rope_positions > 0 && g.rope_positions <= kRopeSmemPos;
 
   const int warp = threadIdx.x >> 5;
@@ -183,6 +242,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_kb = (g.K + kBlockK - 1) / kBlockK;
   const int tiles_per_z = g.m_tiles * g.n_tiles;
 
+  // Register budget: 384 x 168 at launch; warps 8..11 shrink to 56 so that the 8 epilogue warps can grow to 224
+  // (8 x 32 x 224 + 4 x 32 x 56 = 64512).
+  if (warp >= kTmaWarp) setmaxnreg_dec<56>();
   if (warp == kTmaWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -279,12 +341,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < kTmaWarp) {
     // ===================== epilogue (warps 0..7) =====================
     // Two warps share each TMEM lane quarter (hardware: warp w may touch lanes 32*(w%4)..+31) and split the
     // tile's columns in halves; one accumulator row per thread.  Per-column vectors (bias, LayerScale gamma)
     // are staged per warp in smem before the accumulator is waited for, TMEM loads are double-buffered and all
     // global loads of a 32-column chunk are issued before its math, so no latency sits on the critical path.
+    setmaxnreg_inc<224>();
     const int quarter = warp & 3;
     const int half = warp >> 2;
     constexpr int kHalfN = BLOCK_N / 2;
@@ -400,19 +463,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (row_ok) {
             const long long off = (c_r + m) * g.ldc + c_c + n_head;
 #pragma unroll
-            for (int i = 0; i < 64; i += 8) store8<OUT_F32>(g.C, off + i, v + i);
+            for (int i = 0; i < 64; i += 8) store8_bf16(g.C, off + i, v + i);
           }
         }
       } else {
-        long long out_row = c_r + m;
-        const float* pe_row = nullptr;
-        if constexpr (MODE == VQ_EPI_PATCH) {
-          const int f = m / g.n_patches;
-          const int idx = m - f * g.n_patches;
-          out_row = (long long)f * g.tokens_per_frame + g.patch_start + idx;
-          pe_row = g.pos_embed + (long long)(1 + idx) * g.N;
-        }
-        const long long io_row = c_r + m;
+        // 32 columns at a time: the raw accumulators (one row per thread) go through a per-warp smem buffer and
+        // come back transposed, kVec consecutive columns per thread and 32 / kVec threads per row, so that every
+        // global access of the warp covers whole 128-byte (f32) / 64-byte (bf16) row segments instead of 32
+        // different lines.  All epilogue math and every global load / store happens in that layout.
+        constexpr int kVec = OUT_F32 ? 4 : 8;            // columns per thread = one 16-byte C access
+        constexpr int kLanesPerRow = 32 / kVec;
+        constexpr int kRowsPerPass = 32 / kLanesPerRow;
+        constexpr int kPasses = 32 / kRowsPerPass;
+        float* stage = stage_vec + warp * kStageWarpFloats;
+        const int cb = (lane % kLanesPerRow) * kVec;     // this thread's first column inside the chunk
+        const int rsub = lane / kLanesPerRow;
+        const int m_warp0 = m_blk * kTileM + (int)cta_rank * kBlockM + quarter * 32;
         constexpr int kChunks = kHalfN / 32;
         uint32_t acc[2][32];
         if (n_base < g.N) tmem_ld32(taddr, acc[0]);
@@ -423,56 +489,86 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_wait_ld();
           if (ch + 1 < kChunks && n0 + 32 < g.N) tmem_ld32(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);
           const uint32_t(&r)[32] = acc[ch & 1];
-          const int groups = min(4, (g.N - n0) >> 3);  // valid 8-column groups in this chunk
-          // ---- issue every global load of the chunk first
-          float addv[32];
-          float auxv[32];
-          if (g.add) {
+          __syncwarp();  // previous chunk's transposed reads are done
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (row_ok && q < groups) load8<OUT_F32>(g.add, io_row * g.ldadd + c_c + n0 + q * 8, addv + q * 8);
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(stage + lane * kStageLd + 4 * k) =
+                make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+          __syncwarp();
+          const int ncol = n0 + cb;
+          const bool col_ok = ncol < g.N;  // N % 8 == 0: a thread's kVec columns are all in or all out
+          float bv[kVec], gv[kVec];
+#pragma unroll
+          for (int e = 0; e < kVec; e += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(my_vec + ch * 32 + cb + e);
+            const float4 g4 = *reinterpret_cast<const float4*>(my_vec + kHalfN + ch * 32 + cb + e);
+            bv[e] = b4.x; bv[e + 1] = b4.y; bv[e + 2] = b4.z; bv[e + 3] = b4.w;
+            gv[e] = g4.x; gv[e + 1] = g4.y; gv[e + 2] = g4.z; gv[e + 3] = g4.w;
           }
-          if constexpr (MODE == VQ_EPI_GELU_BWD) {
+          // ---- every global load of the chunk first
+          float addv[kPasses][kVec];
+          float auxv[kPasses][kVec];
+          long long orow[kPasses];
+          bool ok[kPasses];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (row_ok && q < groups) load8<false>(g.aux, io_row * g.ldaux + c_c + n0 + q * 8, auxv + q * 8);
+          for (int ps = 0; ps < kPasses; ++ps) {
+            const int m = m_warp0 + ps * kRowsPerPass + rsub;
+            ok[ps] = col_ok && m < g.M;
+            const long long io_row = c_r + m;
+            orow[ps] = io_row;
+            if constexpr (MODE == VQ_EPI_PATCH) {
+              const int f = m / g.n_patches;
+              const int idx = m - f * g.n_patches;
+              orow[ps] = (long long)f * g.tokens_per_frame + g.patch_start + idx;
+              if (ok[ps]) loadv<true>(g.pos_embed, (long long)(1 + idx) * g.N + ncol, auxv[ps]);
+            }
+            if (g.add && ok[ps]) loadv<OUT_F32>(g.add, io_row * g.ldadd + c_c + ncol, addv[ps]);
+            if constexpr (MODE == VQ_EPI_GELU_BWD) {
+              if (ok[ps]) loadv<false>(g.aux, io_row * g.ldaux + c_c + ncol, auxv[ps]);
+            }
           }
-          if constexpr (MODE == VQ_EPI_PATCH) {
+          // ---- math + store
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (row_ok && q < groups) load8<true>(pe_row, n0 + q * 8, auxv + q * 8);
-          }
-          // ---- math + store, 8 columns at a time
+          for (int ps = 0; ps < kPasses; ++ps) {
+            float v[kVec];
+            const float* srow = stage + (ps * kRowsPerPass + rsub) * kStageLd + cb;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[8];
-            const float* bv = my_vec + ch * 32 + q * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q * 8 + i]) * g.alpha + bv[i];
-            if (!(row_ok && q < groups)) continue;
+            for (int e = 0; e < kVec; e += 4) {
+              const float4 a4 = *reinterpret_cast<const float4*>(srow + e);
+              v[e] = a4.x * g.alpha + bv[e];
+              v[e + 1] = a4.y * g.alpha + bv[e + 1];
+              v[e + 2] = a4.z * g.alpha + bv[e + 2];
+              v[e + 3] = a4.w * g.alpha + bv[e + 3];
+            }
+            if (!ok[ps]) continue;
             if constexpr (MODE == VQ_EPI_GELU) {
-              if (g.aux) store8<false>(g.aux, io_row * g.ldaux + c_c + n0 + q * 8, v);
+              if (g.aux) storev<false>(g.aux, orow[ps] * g.ldaux + c_c + ncol, v);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+              for (int e = 0; e < kVec; e += 2) {
+                const float2 y = gelu2(make_float2(v[e], v[e + 1]));
+                v[e] = y.x; v[e + 1] = y.y;
+              }
             }
             if constexpr (MODE == VQ_EPI_GELU_BWD) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(auxv[q * 8 + i]);
+              for (int e = 0; e < kVec; e += 2) {
+                const float2 d = gelu_grad2(make_float2(auxv[ps][e], auxv[ps][e + 1]));
+                v[e] *= d.x; v[e + 1] *= d.y;
+              }
             }
             if constexpr (MODE == VQ_EPI_PATCH) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += auxv[q * 8 + i];
+              for (int e = 0; e < kVec; ++e) v[e] += auxv[ps][e];
             }
             if (g.gamma) {
-              const float* gv = my_vec + kHalfN + ch * 32 + q * 8;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] *= gv[i];
+              for (int e = 0; e < kVec; ++e) v[e] *= gv[e];
             }
             if (g.add) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += addv[q * 8 + i];
+              for (int e = 0; e < kVec; ++e) v[e] += addv[ps][e];
             }
-            store8<OUT_F32>(g.C, out_row * g.ldc + c_c + n0 + q * 8, v);
+            storev<OUT_F32>(g.C, orow[ps] * g.ldc + c_c + ncol, v);
           }
         }
       }
