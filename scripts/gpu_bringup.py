@@ -98,7 +98,7 @@ def case_gemm(M, N, K, a_major=0, b_major=0, epi="linear", out_f32=False, timing
     return ok, msg
 
 
-def case_attn(n_seq, L, heads, timing=False):
+def case_attn(n_seq, L, heads, timing=False, qscale=2.0):
     import torch
 
     from vggt_qwen3_b200 import ops
@@ -106,7 +106,7 @@ def case_attn(n_seq, L, heads, timing=False):
     g = torch.Generator(device="cuda").manual_seed(2)
     HD = heads * 64
     qkv = torch.randn(n_seq * L, 3 * HD, device="cuda", generator=g)
-    qkv[:, :HD] *= 2.0  # sharper softmax
+    qkv[:, :HD] *= qscale  # sharper softmax
     qkv = qkv.bfloat16()
     q, k, v = (qkv[:, i * HD:(i + 1) * HD].float().view(n_seq, L, heads, 64).transpose(1, 2) for i in range(3))
     # kernel convention: q is pre-scaled by log2(e)/sqrt(d); softmax base 2  => plain softmax of q.k * ln2
@@ -173,6 +173,13 @@ CASES = {
     "attn_128": lambda: case_attn(1, 128, 1),
     "attn_256": lambda: case_attn(1, 256, 2),
     "attn_ragged_small": lambda: case_attn(2, 200, 2),
+    "attn_l50": lambda: case_attn(3, 50, 1),
+    "attn_l64": lambda: case_attn(2, 64, 2),
+    "attn_l65": lambda: case_attn(2, 65, 2),
+    "attn_l129": lambda: case_attn(2, 129, 1),
+    "attn_l300": lambda: case_attn(2, 300, 3),
+    "attn_l1374_sharp": lambda: case_attn(2, 1374, 2, qscale=12.0),
+    "attn_l2000_flat": lambda: case_attn(1, 2000, 2, qscale=0.05),
     "attn_frame": lambda: case_attn(8, 1374, 16, timing=True),
     "attn_global8": lambda: case_attn(1, 8 * 1374, 16, timing=True),
 }

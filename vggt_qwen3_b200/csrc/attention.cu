@@ -1,18 +1,33 @@
 // vq_attention_fwd: flash-style non-causal attention for head_dim 64 on tcgen05 / TMEM (sm_100a).
 //
-// One CTA = one (sequence, head, block of 256 query rows) = two 128-row query tiles that ping-pong
-// on the tensor core while each tile's softmax warpgroup works:
+// One CTA = one (sequence, head, block of 256 query rows) = two 128-row query tiles.  Every query tile is served by
+// TWO independent flash-attention streams, one per half of each 128-key K/V stage, so four streams run concurrently:
 //
-//   warps 0..3    softmax warpgroup of query tile 0 : one thread per query row
-//   warps 4..7    softmax warpgroup of query tile 1
-//   warp 8        TMA producer: Q tiles once, then K_j / V_j (128 keys x 64) through a 4-stage ring
-//   warp 9        MMA issuer (whole warp runs the loop, one elected lane issues tcgen05):
-//                                         S_t = Q_t K_j^T   (SS, 128x128x64, accumulator in TMEM)
-//                                         O_t += P_t V_j    (TS: P read from TMEM, V MN-major in smem)
-//                 (highest active warp id: the scheduler favours it over the busy softmax warps)
+//   stream x = 2 * q_tile + kv_half      S_x = Q_t K_{j,h}^T   (SS MMA 128 x 64 x 64, accumulator in TMEM)
+//                                         P_x = exp2(S_x - m_x) (softmax warpgroup x, one thread per query row)
+//                                         O_x += P_x V_{j,h}    (TS MMA: P read from TMEM, V MN-major in smem)
 //
-// TMEM columns (512): S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512).
-// q is pre-scaled by log2(e)/sqrt(64) in the QKV GEMM epilogue, so probabilities are exp2(s - max).
+//   warps 0..15   four softmax warpgroups (stream = warp / 4, TMEM lane quarter = warp % 4)
+//   warp 16       TMA producer: Q tiles once, then K_j / V_j (128 keys x 64) through a 4-stage ring
+//   warp 17       MMA issuer (whole warp runs the loop, one elected lane issues tcgen05)
+//   warps 18..19  idle (setmaxnreg is warpgroup-wide: the fifth warpgroup is complete)
+//
+// Why four streams: at head_dim 64 the kernel is bound by the MUFU (16 ex2/clk/SM), not by the tensor core
+// (a 128 x 128 score tile costs 512 tensor clocks but 1024 MUFU clocks).  One warp per scheduler cannot keep the MUFU
+// busy while it also waits for TMEM loads, barriers and the MMA round trip; four independent warps per scheduler can.
+// Each stream keeps its own running reference m_x, row sum l_x and accumulator O_x; the two streams of a query tile
+// are merged once at the end (through smem).  The streams never synchronise with each other inside the loop.
+//
+// Further MUFU relief:
+//  * a fixed fraction of the exponentials (kEmuOf8 pairs out of every 8) is computed on the FMA pipe:
+//    Cody-Waite split x = n + f, degree-3 polynomial for 2^f (7.5e-5 relative error, bf16 P carries 3.9e-3),
+//    2^n added into the exponent field; packed fp32 (FFMA2 / FADD2) keeps the issue cost down;
+//  * lazy rescaling: the reference m_x only moves when the row maximum exceeds it by more than 2^8, so the
+//    O_x *= alpha round trip through TMEM (and its exp) happens a handful of times per row instead of per tile.
+//
+// TMEM columns (512): stream x owns [128x, 128x + 128): S_x (64 fp32 columns, overwritten in place by the packed
+// bf16 P_x in its first 32 columns) and O_x (64 columns).
+// q is pre-scaled by log2(e)/sqrt(64) in the QKV GEMM epilogue, so probabilities are exp2(s - m).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -21,48 +36,116 @@
 namespace vq {
 
 constexpr int kTileQ = 128;
-constexpr int kTileKV = 128;
+constexpr int kTileKV = 128;   // keys per TMA stage
+constexpr int kHalfKV = 64;    // keys per stream step
 constexpr int kHeadDim = 64;
-constexpr int kAttnThreads = 384;
+constexpr int kStreams = 4;
+constexpr int kAttnTmaWarp = 16;
+constexpr int kAttnMmaWarp = 17;
+constexpr int kAttnThreads = 640;
 constexpr int kKVStages = 4;
 constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: 128 rows x 128 B
-constexpr int kAttnSmemBytes = 2 * kTileBytes + 2 * kKVStages * kTileBytes + 1024 + 256;
+constexpr int kMlBytes = 2 * kTileQ * 8;        // (m, l) of the odd streams for the final merge
+constexpr int kAttnSmemBytes = 2 * kTileBytes + 2 * kKVStages * kTileBytes + 1024 + 256 + kMlBytes;
+constexpr float kRescaleThreshold = 8.0f;       // log2 units: P <= 2^8
 
 struct AttnArgs {
-  long long* trace;  // debug: clock64() timestamps of CTA (0,0,0) (nullptr in production)
   void* out;
   int seq_len;
   int heads;
   int n_kv_tiles;
 };
 
-// trace layout: [role (0 = MMA thread, 1 = softmax warp 4 lane 0, 2 = softmax warp 8 lane 0)][iteration < 32][event < 8]
-#define VQ_TRACE(role, j, ev)                                                                     \
-  do {                                                                                            \
-    if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 32)            \
-      g.trace[((role) * 32 + (j)) * 8 + (ev)] = clock64();                                        \
-  } while (0)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "add.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 
-template <int DBG>
+// 2^x for x <= ~16 on the FMA / ALU pipes (no MUFU): x = n + f with n = rint(x), f in [-0.5, 0.5].
+__device__ __forceinline__ float2 exp2_emulated(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);  // keeps the result a normal number; 2^-125 is zero for every purpose here
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 xr = add2(x, splat(12582912.0f));   // 1.5 * 2^23: the low mantissa bits now hold n
+  const float2 n = add2(xr, splat(-12582912.0f));
+  const float2 f = fma2(n, splat(-1.0f), x);
+  float2 p = splat(5.517166853e-02f);
+  p = fma2(p, f, splat(2.426111400e-01f));
+  p = fma2(p, f, splat(6.932609677e-01f));
+  p = fma2(p, f, splat(9.999280572e-01f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xr.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xr.y) << 23));
+  return r;
+}
+
+// p[32] (packed bf16 pairs) = exp2(s[64] - m); returns the row sum of the fp32 values.
+// EMU of every 8 pairs go through exp2_emulated, the rest through MUFU.EX2.
+template <int EMU, int DBG = 0>
+__device__ __forceinline__ float exp_row(const float (&s)[64], float m, uint32_t (&p)[32]) {
+  const float2 neg_m = splat(-m);
+  float2 acc0 = splat(0.f), acc1 = splat(0.f);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float2 x = add2(make_float2(s[2 * i], s[2 * i + 1]), neg_m);
+    float2 e;
+    if ((i & 7) < EMU) {
+      e = exp2_emulated(x);
+    } else if (DBG & 1) {  // timing experiment: no MUFU
+      e = x;
+    } else {
+      e.x = ex2_approx(x.x);
+      e.y = ex2_approx(x.y);
+    }
+    if (i & 1) acc1 = add2(acc1, e);
+    else acc0 = add2(acc0, e);
+    p[i] = pack_bf16x2(e.x, e.y);
+  }
+  const float2 a = add2(acc0, acc1);
+  return a.x + a.y;
+}
+
+// DBG (timing experiments only, results are wrong): 1 no MUFU, 2 no TMEM load of S, 4 no P store, 8 no MMAs, 16 no max
+template <int EMU, int DBG>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_q = smem_base;                               // 2 tiles
-  const uint32_t smem_k = smem_base + 2 * kTileBytes;              // kKVStages tiles
+  const uint32_t smem_k = smem_base + 2 * kTileBytes;              // kKVStages tiles (reused for the final merge)
   const uint32_t smem_v = smem_k + kKVStages * kTileBytes;         // kKVStages tiles
   const uint32_t bar_base = smem_v + kKVStages * kTileBytes;
   const uint32_t bar_qfull = bar_base;
   const uint32_t bar_kfull = bar_base + 8;
   const uint32_t bar_vfull = bar_kfull + 8 * kKVStages;
   const uint32_t bar_kvempty = bar_vfull + 8 * kKVStages;
-  const uint32_t bar_sfull = bar_kvempty + 8 * kKVStages;  // [2]
-  const uint32_t bar_pfull = bar_sfull + 16;               // [2]
-  const uint32_t bar_odone = bar_pfull + 16;               // [2]
-  const uint32_t bar_sfree = bar_odone + 16;               // [2] softmax has S_t in registers: S_t may be overwritten
-  const uint32_t bar_token = bar_sfree + 16;               // [2] MUFU token: warpgroup t may run its exp phase
-  const uint32_t tmem_slot = bar_token + 16;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const uint32_t bar_sfull = bar_kvempty + 8 * kKVStages;  // [4] S_x(j) is in TMEM
+  const uint32_t bar_pfull = bar_sfull + 8 * kStreams;     // [4] P_x(j) is in TMEM
+  const uint32_t bar_odone = bar_pfull + 8 * kStreams;     // [4] every MMA of stream x has retired
+  const uint32_t tmem_slot = bar_odone + 8 * kStreams;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to smem_base
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  float* ml_buf = reinterpret_cast<float*>(smem_gen + (bar_base + 256 - smem_base));   // [2 tiles][128 rows][m, l]
+  float* merge_buf = reinterpret_cast<float*>(smem_gen + (smem_k - smem_base));        // [2 tiles][128 rows][64] f32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,9 +156,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
   const int seq_row0 = seq * L;
   const int q_row0 = qb * 2 * kTileQ;                        // within the sequence
   const int n_qtiles = (q_row0 + kTileQ < L) ? 2 : 1;        // second tile may be entirely past the end
+  const int n_streams = 2 * n_qtiles;
   const int n_kv = g.n_kv_tiles;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kAttnTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_qfull, 1);
     for (int s = 0; s < kKVStages; ++s) {
@@ -83,16 +167,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
       mbar_init(bar_vfull + 8 * s, 1);
       mbar_init(bar_kvempty + 8 * s, 1);
     }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(bar_sfull + 8 * t, 1);
-      mbar_init(bar_pfull + 8 * t, 4);   // one elected lane per softmax warp
-      mbar_init(bar_odone + 8 * t, 1);
-      mbar_init(bar_sfree + 8 * t, 4);
-      mbar_init(bar_token + 8 * t, 4);
+    for (int x = 0; x < kStreams; ++x) {
+      mbar_init(bar_sfull + 8 * x, 1);
+      mbar_init(bar_pfull + 8 * x, 4);   // one elected lane per softmax warp
+      mbar_init(bar_odone + 8 * x, 1);
     }
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == kAttnMmaWarp) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -101,9 +183,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp >= 8) {
-    setmaxnreg_dec<56>();
-    if (warp == 8 && lane == 0) {
+  if (warp >= kAttnTmaWarp) {
+    setmaxnreg_dec<32>();
+    if (warp == kAttnTmaWarp && lane == 0) {
       // ===================== TMA producer =====================
       mbar_arrive_expect_tx(bar_qfull, n_qtiles * kTileBytes);
       for (int t = 0; t < n_qtiles; ++t)
@@ -122,70 +204,58 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
                     2 * HD + head * kHeadDim, row);
         if (++stage == kKVStages) { stage = 0; phase ^= 1; }
       }
-    } else if (warp == 9) {
+    } else if (warp == kAttnMmaWarp) {
       // ===================== MMA issuer =====================
       // Every lane runs the control flow (waits, descriptor arithmetic stay warp-uniform); only the tcgen05
-      // instructions themselves are predicated on one elected lane.
-      const uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, 0, 0);
+      // instructions themselves are predicated on one elected lane.  tcgen05.mma instructions of one thread
+      // execute in issue order, which is what makes the in-place S -> P reuse safe: S_x(j+1) is issued after
+      // P_x(j) V_j and therefore cannot overwrite P_x(j) before it has been read.
+      const uint32_t idesc_s = make_idesc_bf16(kTileQ, kHalfKV, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(kTileQ, kHeadDim, 0, 1);  // V is MN-major (d contiguous)
       const uint64_t desc_q = make_smem_desc(smem_q, 16, 1024);
       const uint64_t desc_k = make_smem_desc(smem_k, 16, 1024);
       const uint64_t desc_v = make_smem_desc(smem_v, 8192, 1024);
-      auto issue_s = [&](int t, int stage) {
+      // descriptor start-address field is in 16-byte units: +2 per 32-byte k-step, +1024 per 16 KB tile,
+      // +512 per 64-row half tile
+      auto issue_s = [&](int x, int stage) {
         if (elect_one()) {
+          const uint64_t a0 = desc_q + (uint64_t)((x >> 1) * (kTileBytes >> 4));
+          const uint64_t b0 = desc_k + (uint64_t)(stage * (kTileBytes >> 4) + (x & 1) * 512);
 #pragma unroll
-          for (int k = 0; k < kHeadDim / 16; ++k) {
-            // descriptor start-address field is in 16-byte units: +2 per 32-byte k-step, +1024 per 16 KB tile
-            const uint64_t adesc = desc_q + (uint64_t)(t * (kTileBytes >> 4) + k * 2);
-            const uint64_t bdesc = desc_k + (uint64_t)(stage * (kTileBytes >> 4) + k * 2);
-            if constexpr ((DBG & 32) == 0) umma_ss(tmem_base + t * 128, adesc, bdesc, idesc_s, k ? 1u : 0u);
-          }
-          umma_commit(bar_sfull + 8 * t);
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            if constexpr ((DBG & 8) == 0)
+              umma_ss(tmem_base + x * 128, a0 + (uint64_t)(k * 2), b0 + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+          umma_commit(bar_sfull + 8 * x);
         }
         __syncwarp();
       };
       mbar_wait(bar_qfull, 0);
       mbar_wait(bar_kfull, 0);
       tc_fence_after();
-      for (int t = 0; t < n_qtiles; ++t) issue_s(t, 0);
-      // Steady state, per kv tile j and query tile t:
-      //   s_free[t](j)  (softmax t holds S_t(j) in registers)  ->  issue S_t(j+1) = Q_t K_{j+1}^T
-      //   p_full[t](j)  (softmax t wrote P_t(j))               ->  issue O_t += P_t(j) V_j
-      // so the next scores are ready before the softmax of the current tile finishes.
+      for (int x = 0; x < n_streams; ++x) issue_s(x, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
         const int nstage = (stage + 1 == kKVStages) ? 0 : stage + 1;
         const uint32_t nphase = (stage + 1 == kKVStages) ? (phase ^ 1) : phase;
-        VQ_TRACE(0, j, 0);
-        if (j + 1 < n_kv) {
-          mbar_wait_fast(bar_kfull + 8 * nstage, nphase);
-          VQ_TRACE(0, j, 1);
-          for (int t = 0; t < n_qtiles; ++t) {
-            mbar_wait_fast(bar_sfree + 8 * t, j & 1);
-            VQ_TRACE(0, j, 2 + t);
-            tc_fence_after();
-            issue_s(t, nstage);
-          }
-        }
+        const bool has_next = j + 1 < n_kv;
+        if (has_next) mbar_wait_fast(bar_kfull + 8 * nstage, nphase);
         mbar_wait_fast(bar_vfull + 8 * stage, phase);
-        VQ_TRACE(0, j, 4);
-        for (int t = 0; t < n_qtiles; ++t) {
-          mbar_wait_fast(bar_pfull + 8 * t, j & 1);
-          VQ_TRACE(0, j, 5 + t);
+        for (int x = 0; x < n_streams; ++x) {
+          mbar_wait_fast(bar_pfull + 8 * x, j & 1);
           tc_fence_after();
           if (elect_one()) {
+            // 16 keys per MMA: 8 TMEM columns of packed bf16 P, 16 smem rows (2048 B = 128 units) of V
+            const uint64_t b0 = desc_v + (uint64_t)(stage * (kTileBytes >> 4) + (x & 1) * 512);
 #pragma unroll
-            for (int k = 0; k < kTileKV / 16; ++k) {
-              // 16 keys per MMA: 8 TMEM columns of packed bf16 P, 16 smem rows (2048 B = 128 units) of V
-              const uint64_t bdesc = desc_v + (uint64_t)(stage * (kTileBytes >> 4) + k * 128);
-              if constexpr ((DBG & 16) == 0)
-                umma_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + k * 8, bdesc, idesc_o,
-                        (j | k) ? 1u : 0u);
-            }
-            umma_commit(bar_odone + 8 * t);
+            for (int k = 0; k < kHalfKV / 16; ++k)
+              if constexpr ((DBG & 8) == 0)
+              umma_ts(tmem_base + x * 128 + 64, tmem_base + x * 128 + k * 8, b0 + (uint64_t)(k * 128), idesc_o,
+                      (j | k) ? 1u : 0u);
+            if (!has_next) umma_commit(bar_odone + 8 * x);
           }
           __syncwarp();
+          if (has_next) issue_s(x, nstage);
         }
         if (elect_one()) umma_commit(bar_kvempty + 8 * stage);
         __syncwarp();
@@ -195,161 +265,143 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
     }
   } else {
     // ===================== softmax warpgroups =====================
-    setmaxnreg_inc<216>();
-    const int t = warp >> 2;
-    if (t < n_qtiles) {
+    setmaxnreg_inc<112>();
+    const int x = warp >> 2;       // stream
+    const int t = x >> 1;          // query tile
+    const int h = x & 1;           // half of each K/V stage
+    if (x < n_streams) {
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;                       // row within the query tile
       const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
-      const uint32_t tS = tmem_base + lane_addr + t * 128;
-      const uint32_t tO = tmem_base + lane_addr + 256 + t * 64;
-      const uint32_t tP = tmem_base + lane_addr + 384 + t * 64;
-      float m_run = -INFINITY, l_run = 0.f;
-      // Ping-pong of the two softmax warpgroups over the MUFU pipe (16 ex2/clk/SM bounds this kernel): a warpgroup
-      // runs its exp phase only while holding the token (mbarrier bar_token[t]), then hands it to the other one,
-      // so one warpgroup's loads / max / pack / TMEM stores overlap the other's exponentials instead of both
-      // competing for the MUFU at the same time and idling it together afterwards.  (A named bar.sync does not
-      // work here: BAR.SYNC.DEFER_BLOCKING lets register-only math run ahead of the barrier.)
-      const bool pingpong = n_qtiles == 2;
-      if (pingpong && t == 1 && lane == 0) mbar_arrive(bar_token);  // warpgroup 0 goes first
+      const uint32_t tS = tmem_base + lane_addr + x * 128;
+      const uint32_t tO = tS + 64;
+      float m_ref = 0.f, l_run = 0.f;
 
-      const int trole = 1 + t;
-      const bool tlane = (warp & 3) == 0 && lane == 0;
       for (int j = 0; j < n_kv; ++j) {
-        if (tlane) VQ_TRACE(trole, j, 0);
-        mbar_wait(bar_sfull + 8 * t, j & 1);
-        if (tlane) VQ_TRACE(trole, j, 1);
+        mbar_wait_trap(bar_sfull + 8 * x, j & 1);
         tc_fence_after();
-        float s[128];
+        float s[64];
         {
-          uint32_t r[32];
+          uint32_t r0[32], r1[32];
+          if constexpr (DBG & 2) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if ((DBG & 4) == 0 || c == 0) {  // timing experiment (DBG & 4): one TMEM load instead of four
-              tmem_ld32(tS + c * 32, r);
-              tmem_wait_ld();
-            }
+            for (int i = 0; i < 32; ++i) { r0[i] = __float_as_uint(float(i + lane + j) * 0.01f); r1[i] = __float_as_uint(float(i - lane - j) * 0.01f); }
+          } else {
+            tmem_ld32(tS, r0);
+            tmem_ld32(tS + 32, r1);
+            tmem_wait_ld();
+          }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) {
+            s[i] = __uint_as_float(r0[i]);
+            s[32 + i] = __uint_as_float(r1[i]);
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_sfree + 8 * t);  // S_t is in registers: the MMA warp may start S_t(j+1)
-        if (tlane) VQ_TRACE(trole, j, 2);
-        const int n_valid = L - j * kTileKV;  // keys of this tile inside the sequence
-        if (n_valid < kTileKV) {
+        const int n_valid = L - j * kTileKV - h * kHalfKV;  // keys of this half tile inside the sequence
+        const bool tail = n_valid < kHalfKV;
+        if (tail) {
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
+          for (int i = 0; i < 64; ++i)
             if (i >= n_valid) s[i] = -INFINITY;
         }
-        // four independent max / sum chains: with two softmax warps per scheduler the dependent-issue latency
-        // of a single 128-long chain would otherwise sit on the critical path
-        float mx4[4] = {s[0], s[1], s[2], s[3]};
+        float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
-        for (int i = 4; i < 128; i += 4) {
-          mx4[0] = fmaxf(mx4[0], s[i]);
-          mx4[1] = fmaxf(mx4[1], s[i + 1]);
-          mx4[2] = fmaxf(mx4[2], s[i + 2]);
-          mx4[3] = fmaxf(mx4[3], s[i + 3]);
+        for (int i = 4; i < 64; i += 4) {
+          mx0 = fmaxf(fmaxf(mx0, s[i]), s[i + 1]);
+          mx1 = fmaxf(fmaxf(mx1, s[i + 2]), s[i + 3]);
         }
-        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        if constexpr (DBG & 2) mx = s[0];  // timing experiment: no row max
-        const float m_new = fmaxf(m_run, mx);
-        const float alpha = ex2_approx(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-        if (tlane) VQ_TRACE(trole, j, 3);
-        float m_use = m_new;
-        if (pingpong) {
-          mbar_wait_fast(bar_token + 8 * t, j & 1);
-          asm volatile("" : "+f"(m_use));  // keep the exponentials behind the token wait
-        }
-        if (tlane) VQ_TRACE(trole, j, 4);
-        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t p[64];
-        // One warp alone reaches only ~70 % of the MUFU rate, two together saturate it: the token is handed over
-        // after kHandoff of the 64 pair-iterations so the other warpgroup's exponentials overlap the tail of ours.
-        constexpr int kHandoff = 40;
+        float mx = fmaxf(mx0, mx1);
+        if constexpr (DBG & 16) mx = s[lane & 63];
+        if (j == 0) {
+          m_ref = (mx == -INFINITY) ? 0.f : mx;   // an entirely masked first half tile: P = 0, l stays 0
+        } else {
+          // lazy rescale: the reference only moves when the row maximum outgrows it by more than 2^8
+          const bool grow = mx > m_ref + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float m_new = grow ? mx : m_ref;
+            const float alpha = ex2_approx(m_ref - m_new);
+            m_ref = m_new;
+            l_run *= alpha;
+            // every MMA issued before S_x(j) -- P_x(j-1) V included -- retired when bar_sfull fired
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          float p0, p1, p2, p3;
-          if constexpr (DBG & 1) {  // timing experiment: no MUFU
-            p0 = s[2 * i] - m_use; p1 = s[2 * i + 1] - m_use; p2 = s[2 * i + 2] - m_use; p3 = s[2 * i + 3] - m_use;
-          } else {
-            p0 = ex2_approx(s[2 * i] - m_use);
-            p1 = ex2_approx(s[2 * i + 1] - m_use);
-            p2 = ex2_approx(s[2 * i + 2] - m_use);
-            p3 = ex2_approx(s[2 * i + 3] - m_use);
-          }
-          sum4[0] += p0;
-          sum4[1] += p1;
-          sum4[2] += p2;
-          sum4[3] += p3;
-          p[i] = pack_bf16x2(p0, p1);
-          p[i + 1] = pack_bf16x2(p2, p3);
-          if (i + 2 == kHandoff && pingpong) {
-            asm volatile("" ::"f"(sum4[0]), "f"(sum4[1]), "f"(sum4[2]), "f"(sum4[3]));
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_token + 8 * (t ^ 1));
-          }
-        }
-        if (tlane) VQ_TRACE(trole, j, 5);
-        const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-        l_run = l_run * alpha + sum;
-
-        if (j > 0) {
-          // PV_{j-1} must have retired before P is overwritten or O is rescaled
-          mbar_wait(bar_odone + 8 * t, (j - 1) & 1);
-          if (tlane) VQ_TRACE(trole, j, 6);
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, m_new > m_run)) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t o[32];
-              tmem_ld32(tO + c * 32, o);
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tO + c * 16, o);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tO + c * 32, o);
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + c * 16, o);
             }
           }
         }
-        {
-          uint32_t(&p_lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&p[0]);
-          uint32_t(&p_hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&p[32]);
-          if constexpr ((DBG & 8) == 0) {  // timing experiment (DBG & 8): no P store
-            tmem_st32(tP, p_lo);
-            tmem_st32(tP + 32, p_hi);
-          }
-        }
+        uint32_t p[32];
+        // masked tiles take the all-MUFU path: ex2(-inf) is exactly 0, the emulation bottoms out at 2^-125
+        const float sum = tail ? exp_row<0, DBG>(s, m_ref, p) : exp_row<EMU, DBG>(s, m_ref, p);
+        l_run += sum;
+        if constexpr ((DBG & 4) == 0) tmem_st32(tS, p);
+        else asm volatile("" ::"r"(p[0]), "r"(p[7]), "r"(p[13]), "r"(p[31]));
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_pfull + 8 * t);
-        if (tlane) VQ_TRACE(trole, j, 7);
-        m_run = m_new;
+        if (lane == 0) mbar_arrive(bar_pfull + 8 * x);
       }
 
-      // ---- epilogue: O / l -> bf16 -> out[row, head*64 .. +64]
-      mbar_wait(bar_odone + 8 * t, (n_kv - 1) & 1);
+      // ---- merge the two streams of this query tile and write O / l -> bf16 -> out[row, head*64 .. +64]
+      mbar_wait_trap(bar_odone + 8 * x, 0);
       tc_fence_after();
-      const float inv_l = 1.0f / l_run;
-      const int q_in_seq = q_row0 + t * kTileQ + row;
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) +
-                           (long long)(seq_row0 + q_in_seq) * HD + head * kHeadDim;
+      float* mrow = merge_buf + (t * kTileQ + row) * 64;
+      float* ml = ml_buf + (t * kTileQ + row) * 2;
+      const int sw = row & 15;  // 16-byte granule swizzle: conflict-free row-per-thread float4 accesses
+      if (h == 1) {
+        // Once any bar_odone has fired every S MMA has retired, so the K ring (merge_buf) is free; the V ring is not.
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tO + c * 32, o);
-        tmem_wait_ld();
-        if (q_in_seq < L) {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[16];
+          tmem_ld16(tO + c * 16, o);
+          tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-            u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-            u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-            u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(dst + c * 32 + i) = u;
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(mrow + (((c * 4 + q4) ^ sw) << 2)) =
+                make_uint4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+        }
+        ml[0] = l_run > 0.f ? m_ref : -INFINITY;  // an empty stream must not raise the merged reference
+        ml[1] = l_run;
+        __threadfence_block();
+        named_bar_arrive(1 + t, 256);
+      } else {
+        named_bar_sync(1 + t, 256);
+        const float m_b = ml[0], l_b = ml[1];
+        const float m = fmaxf(m_ref, m_b);
+        const float fa = ex2_approx(m_ref - m), fb = ex2_approx(m_b - m);
+        const float inv_l = 1.0f / (l_run * fa + l_b * fb);
+        const float wa = fa * inv_l, wb = fb * inv_l;
+        const int q_in_seq = q_row0 + t * kTileQ + row;
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) +
+                             (long long)(seq_row0 + q_in_seq) * HD + head * kHeadDim;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[16];
+          tmem_ld16(tO + c * 16, o);
+          tmem_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 b = *reinterpret_cast<const float4*>(mrow + (((c * 4 + q4) ^ sw) << 2));
+            v[4 * q4 + 0] = __uint_as_float(o[4 * q4 + 0]) * wa + b.x * wb;
+            v[4 * q4 + 1] = __uint_as_float(o[4 * q4 + 1]) * wa + b.y * wb;
+            v[4 * q4 + 2] = __uint_as_float(o[4 * q4 + 2]) * wa + b.z * wb;
+            v[4 * q4 + 3] = __uint_as_float(o[4 * q4 + 3]) * wa + b.w * wb;
+          }
+          if (q_in_seq < L) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(v[i + 0], v[i + 1]);
+              u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+              u.z = pack_bf16x2(v[i + 4], v[i + 5]);
+              u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+              *reinterpret_cast<uint4*>(dst + c * 16 + i) = u;
+            }
           }
         }
       }
@@ -358,16 +410,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kAttnMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
 }  // namespace vq
-
-static long long* g_attn_trace = nullptr;
-extern "C" void vq_debug_set_attention_trace(long long* device_buf) { g_attn_trace = device_buf; }
 
 extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32_t seq_len,
                                 int32_t heads, vq_stream_t stream_) {
@@ -383,21 +432,35 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
   const CUtensorMap* tm = get_tmap_2d_bf16(qkv, 3ull * HD, (uint64_t)rows, 3ull * HD, 64, 128);
   if (!tm) return VQ_ERR_CUDA;
 
+  // pairs (of every 8) whose exponentials run on the FMA pipe instead of the MUFU; tunable for experiments
+  static const int emu = [] {
+    const char* e = getenv("VQ_ATTN_EMU");
+    const int v = e ? atoi(e) : 2;
+    return v < 0 ? 0 : v > 4 ? 4 : v;
+  }();
   static const int dbg = [] {
     const char* e = getenv("VQ_ATTN_DBG");  // timing experiments only (results are wrong when non-zero)
     return e ? atoi(e) : 0;
   }();
-  auto kern = dbg == 1 ? attention_fwd_kernel<1> : dbg == 4 ? attention_fwd_kernel<4>
-            : dbg == 8 ? attention_fwd_kernel<8> : dbg == 15 ? attention_fwd_kernel<15>
-            : dbg == 31 ? attention_fwd_kernel<31> : dbg == 47 ? attention_fwd_kernel<47>
-            : dbg == 63 ? attention_fwd_kernel<63> : attention_fwd_kernel<0>;
+  auto kern = emu == 0 ? attention_fwd_kernel<0, 0> : emu == 1 ? attention_fwd_kernel<1, 0>
+            : emu == 2 ? attention_fwd_kernel<2, 0> : emu == 3 ? attention_fwd_kernel<3, 0> : attention_fwd_kernel<4, 0>;
+  switch (dbg) {
+    case 1: kern = attention_fwd_kernel<0, 1>; break;
+    case 2: kern = attention_fwd_kernel<0, 2>; break;
+    case 4: kern = attention_fwd_kernel<0, 4>; break;
+    case 8: kern = attention_fwd_kernel<0, 8>; break;
+    case 16: kern = attention_fwd_kernel<0, 16>; break;
+    case 9: kern = attention_fwd_kernel<0, 9>; break;
+    case 23: kern = attention_fwd_kernel<0, 23>; break;
+    case 31: kern = attention_fwd_kernel<0, 31>; break;
+    default: break;
+  }
   static bool configured = false;
   if (!configured) {
     VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     configured = true;
   }
   AttnArgs g;
-  g.trace = g_attn_trace;
   g.out = out;
   g.seq_len = seq_len;
   g.heads = heads;
