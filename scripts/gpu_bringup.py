@@ -181,7 +181,9 @@ CASES = {
     "attn_l1374_sharp": lambda: case_attn(2, 1374, 2, qscale=12.0),
     "attn_l2000_flat": lambda: case_attn(1, 2000, 2, qscale=0.05),
     "attn_frame": lambda: case_attn(8, 1374, 16, timing=True),
+    "attn_frame32": lambda: case_attn(32, 1374, 16, timing=True),
     "attn_global8": lambda: case_attn(1, 8 * 1374, 16, timing=True),
+    "attn_global8x4": lambda: case_attn(4, 8 * 1374, 16, timing=True),
 }
 
 

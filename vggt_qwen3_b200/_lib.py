@@ -9,7 +9,8 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libvq_b200.so"
+# VQ_B200_LIB: load an experimental build of the same library (kernel tuning); the default is the in-tree build
+LIB_PATH = Path(os.environ["VQ_B200_LIB"]) if os.environ.get("VQ_B200_LIB") else _PKG / "libvq_b200.so"
 
 VQ_BF16, VQ_F32 = 0, 1
 EPI_LINEAR, EPI_GELU, EPI_GELU_BWD, EPI_QKV_ROPE, EPI_PATCH = 0, 1, 2, 3, 4
@@ -144,6 +145,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vq_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.vq_attention_fwd.restype = C.c_int
     lib.vq_attention_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.vq_attention_tune.restype = C.c_int
+    lib.vq_attention_tune.argtypes = [C.c_int32, C.c_int32]
     lib.vq_aggregator_workspace_bytes.restype = C.c_size_t
     lib.vq_aggregator_workspace_bytes.argtypes = [C.POINTER(AggregatorCfg)]
     lib.vq_launch_count.restype = C.c_longlong

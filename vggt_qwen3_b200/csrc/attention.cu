@@ -39,15 +39,45 @@ constexpr int kTileQ = 128;
 constexpr int kTileKV = 128;   // keys per TMA stage
 constexpr int kHalfKV = 64;    // keys per stream step
 constexpr int kHeadDim = 64;
-constexpr int kStreams = 4;
-constexpr int kAttnTmaWarp = 16;
-constexpr int kAttnMmaWarp = 17;
-constexpr int kAttnThreads = 640;
-constexpr int kKVStages = 4;
 constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: 128 rows x 128 B
-constexpr int kMlBytes = 2 * kTileQ * 8;        // (m, l) of the odd streams for the final merge
-constexpr int kAttnSmemBytes = 2 * kTileBytes + 2 * kKVStages * kTileBytes + 1024 + 256 + kMlBytes;
 constexpr float kRescaleThreshold = 8.0f;       // log2 units: P <= 2^8
+
+// QT = query tiles per CTA.
+//   QT = 2: 256 query rows, four streams, 640 threads, one CTA per SM, 4-stage K/V ring (long sequences);
+//   QT = 1: 128 query rows, two streams, 384 threads, TWO CTAs per SM (256 TMEM columns, half the register file and
+//           half the shared memory each): finer query granularity for ragged L (1374 = 10.7 tiles) and the fill /
+//           drain of one CTA overlaps the steady state of its neighbour (short sequences: frame attention).
+#ifndef VQ_QT1_STAGES
+#define VQ_QT1_STAGES 3
+#endif
+#ifndef VQ_QT1_MINBLOCKS
+#define VQ_QT1_MINBLOCKS 2
+#endif
+#ifndef VQ_QT1_ML_ALIAS
+#define VQ_QT1_ML_ALIAS 1
+#endif
+template <int QT>
+struct AttnCfg {
+  static constexpr int kStreams = 2 * QT;
+  static constexpr int kTmaWarp = 8 * QT;          // first warp after the softmax warpgroups
+  static constexpr int kMmaWarp = 8 * QT + 1;      // QT issuing warps: kMmaWarp .. kMmaWarp + QT - 1
+  static constexpr int kThreads = (8 * QT + 4) * 32;
+  static constexpr int kStages = QT == 2 ? 4 : VQ_QT1_STAGES;
+  static constexpr int kTmemCols = 256 * QT;
+  static constexpr int kMinBlocks = QT == 2 ? 1 : VQ_QT1_MINBLOCKS;
+  static constexpr bool kMlAlias = QT == 1 && VQ_QT1_ML_ALIAS;
+  // setmaxnreg moves registers inside the CTA's own launch-time allocation (threads x launch registers), not the
+  // SM's: 640 x 96 = 512 x 112 + 128 x 32 (QT = 2);  384 x 80 >= 256 x 104 + 128 x 24 (QT = 1, two CTAs per SM).
+  static constexpr int kRegsSoftmax = (QT == 2 || kMinBlocks == 1) ? 112 : 104;
+  static constexpr int kRegsLow = (QT == 2 || kMinBlocks == 1) ? 32 : 24;
+  static constexpr int kMlBytes = QT * kTileQ * 8;  // (m, l) of the odd streams for the final merge
+  // QT = 1: (m, l) aliases the Q tile (dead once the S MMAs have retired) so that two CTAs fit one SM
+  static constexpr int kNeeded = QT * kTileBytes + 2 * kStages * kTileBytes + 256 + (kMlAlias ? 0 : kMlBytes);
+  // 2 CTAs / SM: (228 KB - 2 x 1 KB reserved) / 2 = 115712 B each; the slack over kNeeded absorbs a base that is
+  // not 1024-byte aligned (the kernel traps if the carve-up does not fit)
+  static constexpr int kSmemBytes = (QT == 2 || kNeeded > 115712) ? kNeeded + 1024 : 115712;
+  static_assert(kNeeded <= kSmemBytes, "smem carve-up");
+};
 
 struct AttnArgs {
   void* out;
@@ -125,13 +155,24 @@ __device__ __forceinline__ float exp_row(const float (&s)[64], float m, uint32_t
 }
 
 // DBG (timing experiments only, results are wrong): 1 no MUFU, 2 no TMEM load of S, 4 no P store, 8 no MMAs, 16 no max
-template <int EMU, int DBG>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+template <int QT, int EMU, int DBG>
+__global__ void __launch_bounds__(AttnCfg<QT>::kThreads, AttnCfg<QT>::kMinBlocks)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g) {
-  extern __shared__ uint8_t smem_raw[];
+  using Cfg = AttnCfg<QT>;
+  constexpr int kStreams = Cfg::kStreams;
+  constexpr int kKVStages = Cfg::kStages;
+  constexpr int kAttnTmaWarp = Cfg::kTmaWarp;
+  constexpr int kAttnMmaWarp = Cfg::kMmaWarp;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_q = smem_base;                               // 2 tiles
-  const uint32_t smem_k = smem_base + 2 * kTileBytes;              // kKVStages tiles (reused for the final merge)
+  if (smem_base - smem_u32(smem_raw) + Cfg::kNeeded > Cfg::kSmemBytes) {  // carve-up does not fit
+#ifdef VQ_TRAP_PRINT
+    if (threadIdx.x == 0) printf("vq: attention smem base 0x%x not aligned enough\n", smem_u32(smem_raw));
+#endif
+    __trap();
+  }
+  const uint32_t smem_q = smem_base;                               // QT tiles
+  const uint32_t smem_k = smem_base + QT * kTileBytes;             // kKVStages tiles (reused for the final merge)
   const uint32_t smem_v = smem_k + kKVStages * kTileBytes;         // kKVStages tiles
   const uint32_t bar_base = smem_v + kKVStages * kTileBytes;
   const uint32_t bar_qfull = bar_base;
@@ -144,18 +185,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
   const uint32_t tmem_slot = bar_odone + 8 * kStreams;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to smem_base
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
-  float* ml_buf = reinterpret_cast<float*>(smem_gen + (bar_base + 256 - smem_base));   // [2 tiles][128 rows][m, l]
-  float* merge_buf = reinterpret_cast<float*>(smem_gen + (smem_k - smem_base));        // [2 tiles][128 rows][64] f32
+  // [QT tiles][128 rows][m, l]: after the barriers (QT = 2) or over the dead Q tile (QT = 1)
+  float* ml_buf = reinterpret_cast<float*>(smem_gen + (Cfg::kMlAlias ? 0u : bar_base + 256 - smem_base));
+  float* merge_buf = reinterpret_cast<float*>(smem_gen + (smem_k - smem_base));        // [QT tiles][128 rows][64] f32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // q-block index is the slowest grid dimension: the (partly empty) last q-blocks are scheduled last
-  const int head = blockIdx.x, seq = blockIdx.y, qb = blockIdx.z;
+  // The q-block index is the FASTEST grid dimension: the CTAs resident at any moment share a handful of (sequence,
+  // head) pairs, so K / V come from HBM once and from L2 for every other q-block (with the head index fastest the
+  // resident set cycles through every sequence's K / V per q-block and re-reads it from HBM each time).
+  const int qb = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int L = g.seq_len;
   const int HD = g.heads * kHeadDim;
   const int seq_row0 = seq * L;
-  const int q_row0 = qb * 2 * kTileQ;                        // within the sequence
-  const int n_qtiles = (q_row0 + kTileQ < L) ? 2 : 1;        // second tile may be entirely past the end
+  const int q_row0 = qb * QT * kTileQ;                       // within the sequence
+  const int n_qtiles = (QT == 2 && q_row0 + kTileQ < L) ? 2 : 1;   // second tile may be entirely past the end
   const int n_streams = 2 * n_qtiles;
   const int n_kv = g.n_kv_tiles;
 
@@ -175,7 +219,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
     fence_barrier_init();
   }
   if (warp == kAttnMmaWarp) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -184,7 +228,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp >= kAttnTmaWarp) {
-    setmaxnreg_dec<32>();
+    setmaxnreg_dec<Cfg::kRegsLow>();
     if (warp == kAttnTmaWarp && lane == 0) {
       // ===================== TMA producer =====================
       mbar_arrive_expect_tx(bar_qfull, n_qtiles * kTileBytes);
@@ -266,7 +310,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
     }
   } else {
     // ===================== softmax warpgroups =====================
-    setmaxnreg_inc<112>();
+    setmaxnreg_inc<Cfg::kRegsSoftmax>();
     const int x = warp >> 2;       // stream
     const int t = x >> 1;          // query tile
     const int h = x & 1;           // half of each K/V stage
@@ -349,12 +393,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
 
       // ---- merge the two streams of this query tile and write O / l -> bf16 -> out[row, head*64 .. +64]
       mbar_wait_trap(bar_odone + 8 * x, 0);
+      // QT = 2: the K ring (merge_buf) is shared with the other query tile, whose S MMAs come from another issuing
+      // warp: any of its odone barriers proves they have retired too
+      if (QT == 2 && h == 1 && n_qtiles == 2) mbar_wait_trap(bar_odone + 8 * (2 * (1 - t)), 0);
       tc_fence_after();
       float* mrow = merge_buf + (t * kTileQ + row) * 64;
       float* ml = ml_buf + (t * kTileQ + row) * 2;
       const int sw = row & 15;  // 16-byte granule swizzle: conflict-free row-per-thread float4 accesses
       if (h == 1) {
-        // Once any bar_odone has fired every S MMA has retired, so the K ring (merge_buf) is free; the V ring is not.
+        // bar_odone of a tile fires after every S MMA of that tile's issuing warp has retired: the K ring (merge_buf)
+        // and this tile's Q tile (ml_buf when QT = 1) are free; the V ring is not.
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t o[16];
@@ -413,11 +461,30 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
   __syncthreads();
   if (warp == kAttnMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
 }  // namespace vq
+
+namespace vq {
+static int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return v < lo ? lo : v > hi ? hi : v;
+}
+// pairs (of every 8) whose exponentials run on the FMA pipe instead of the MUFU
+static int g_attn_emu = env_int("VQ_ATTN_EMU", 2, 0, 4);
+// query tiles per CTA: 0 = by sequence length (1 up to kShortSeq keys, 2 above); 1 / 2 force a variant
+static int g_attn_qt = env_int("VQ_ATTN_QT", 0, 0, 2);
+static int g_attn_dbg = env_int("VQ_ATTN_DBG", 0, 0, 31);  // timing experiments only (results are wrong when non-zero)
+}  // namespace vq
+
+extern "C" int vq_attention_tune(int32_t q_tiles_per_cta, int32_t emu_pairs) {
+  if (q_tiles_per_cta >= 0) vq::g_attn_qt = q_tiles_per_cta > 2 ? 2 : q_tiles_per_cta;
+  if (emu_pairs >= 0) vq::g_attn_emu = emu_pairs > 4 ? 4 : emu_pairs;
+  return VQ_OK;
+}
 
 extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32_t seq_len,
                                 int32_t heads, vq_stream_t stream_) {
@@ -425,7 +492,7 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(qkv && out, "qkv/out must be non-null");
   VQ_CHECK_ARG(n_seq > 0 && seq_len > 0 && heads > 0, "n_seq, seq_len, heads must be positive");
-  VQ_CHECK_ARG(n_seq <= 65535 && (seq_len + 2 * kTileQ - 1) / (2 * kTileQ) <= 65535, "grid limits");
+  VQ_CHECK_ARG(n_seq <= 65535 && heads <= 65535, "grid limits");
   VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(out) % 16) == 0, "out alignment");
   const long long rows = (long long)n_seq * seq_len;
   VQ_CHECK_ARG(rows + 512 < INT32_MAX, "too many rows");
@@ -433,45 +500,51 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
   const CUtensorMap* tm = get_tmap_2d_bf16(qkv, 3ull * HD, (uint64_t)rows, 3ull * HD, 64, 128);
   if (!tm) return VQ_ERR_CUDA;
 
-  // pairs (of every 8) whose exponentials run on the FMA pipe instead of the MUFU; tunable for experiments
-  static const int emu = [] {
-    const char* e = getenv("VQ_ATTN_EMU");
-    const int v = e ? atoi(e) : 2;
-    return v < 0 ? 0 : v > 4 ? 4 : v;
-  }();
-  static const int dbg = [] {
-    const char* e = getenv("VQ_ATTN_DBG");  // timing experiments only (results are wrong when non-zero)
-    return e ? atoi(e) : 0;
-  }();
-  auto kern = emu == 0 ? attention_fwd_kernel<0, 0> : emu == 1 ? attention_fwd_kernel<1, 0>
-            : emu == 2 ? attention_fwd_kernel<2, 0> : emu == 3 ? attention_fwd_kernel<3, 0> : attention_fwd_kernel<4, 0>;
-  switch (dbg) {
-    case 1: kern = attention_fwd_kernel<0, 1>; break;
-    case 2: kern = attention_fwd_kernel<0, 2>; break;
-    case 4: kern = attention_fwd_kernel<0, 4>; break;
-    case 8: kern = attention_fwd_kernel<0, 8>; break;
-    case 16: kern = attention_fwd_kernel<0, 16>; break;
-    case 9: kern = attention_fwd_kernel<0, 9>; break;
-    case 23: kern = attention_fwd_kernel<0, 23>; break;
-    case 31: kern = attention_fwd_kernel<0, 31>; break;
-    default: break;
+  const int emu = g_attn_emu;
+  const int dbg = g_attn_dbg;
+  const int force_qt = g_attn_qt;
+  constexpr int kShortSeq = 4096;
+  const int qt = (force_qt == 1 || force_qt == 2) ? force_qt : (seq_len <= kShortSeq ? 1 : 2);
+
+  using Kern = void (*)(const CUtensorMap, const AttnArgs);
+  Kern kern = nullptr;
+  if (qt == 2) {
+    kern = emu == 0 ? attention_fwd_kernel<2, 0, 0> : emu == 1 ? attention_fwd_kernel<2, 1, 0>
+         : emu == 2 ? attention_fwd_kernel<2, 2, 0> : emu == 3 ? attention_fwd_kernel<2, 3, 0>
+                                                                : attention_fwd_kernel<2, 4, 0>;
+    switch (dbg) {
+      case 1: kern = attention_fwd_kernel<2, 0, 1>; break;
+      case 2: kern = attention_fwd_kernel<2, 0, 2>; break;
+      case 4: kern = attention_fwd_kernel<2, 0, 4>; break;
+      case 8: kern = attention_fwd_kernel<2, 0, 8>; break;
+      case 16: kern = attention_fwd_kernel<2, 0, 16>; break;
+      default: break;
+    }
+  } else {
+    kern = emu == 0 ? attention_fwd_kernel<1, 0, 0> : emu == 1 ? attention_fwd_kernel<1, 1, 0>
+         : emu == 2 ? attention_fwd_kernel<1, 2, 0> : emu == 3 ? attention_fwd_kernel<1, 3, 0>
+                                                                : attention_fwd_kernel<1, 4, 0>;
   }
-  static bool configured = false;
-  if (!configured) {
-    VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-    configured = true;
+  const int smem_bytes = qt == 2 ? AttnCfg<2>::kSmemBytes : AttnCfg<1>::kSmemBytes;
+  const int threads = qt == 2 ? AttnCfg<2>::kThreads : AttnCfg<1>::kThreads;
+  static bool configured[3][5] = {};
+  if (!configured[qt][emu] || dbg) {
+    VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
+    configured[qt][emu] = true;
   }
   AttnArgs g;
   g.out = out;
   g.seq_len = seq_len;
   g.heads = heads;
   g.n_kv_tiles = (seq_len + kTileKV - 1) / kTileKV;
-  dim3 grid(heads, n_seq, (seq_len + 2 * kTileQ - 1) / (2 * kTileQ));
+  dim3 grid((seq_len + qt * kTileQ - 1) / (qt * kTileQ), heads, n_seq);
   {
     const double flops = 4.0 * n_seq * heads * (double)seq_len * seq_len * kHeadDim;
     const double bytes = 2.0 * (double)rows * HD * 4.0;  // q, k, v read once + out written (bf16)
     LaunchScope scope(kKindAttention, "attention_fwd", n_seq, seq_len, heads, flops, bytes, stream);
-    kern<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(*tm, g);
+    kern<<<grid, threads, smem_bytes, stream>>>(*tm, g);
   }
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;

@@ -353,8 +353,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int kHalfN = BLOCK_N / 2;
     const int row_in_tile = quarter * 32 + lane;
     float* my_vec = epi_vec + warp * (2 * kHalfN);  // [bias | gamma] x kHalfN, private to this warp
+    // The residual (`add`) block of a tile is known long before its accumulator: pull it into L2 one tile ahead so
+    // that the epilogue's loads are L2 hits instead of HBM round trips (the f32 residual epilogue is latency-bound).
+    auto prefetch_add = [&](int t) {
+      if (MODE == VQ_EPI_QKV_ROPE || !g.add || t >= g.total_tiles) return;
+      const int z = t / tiles_per_z;
+      const int rem = t - z * tiles_per_z;
+      const int m_blk = rem / g.n_tiles;
+      const int n_blk = rem - m_blk * g.n_tiles;
+      const int z0 = z / g.Z1, z1 = z - z0 * g.Z1;
+      const long long c_r = z0 * g.c_r0 + z1 * g.c_r1, c_c = z0 * g.c_c0 + z1 * g.c_c1;
+      const int m0 = m_blk * kTileM + (int)cta_rank * kBlockM + quarter * 32;
+      const int n0 = n_blk * BLOCK_N + half * kHalfN;
+      constexpr int kLineElts = OUT_F32 ? 32 : 64;   // elements per 128-byte line
+      constexpr int kLinesPerRow = kHalfN / kLineElts;
+      const char* base = reinterpret_cast<const char*>(g.add);
+#pragma unroll
+      for (int i = lane; i < 32 * kLinesPerRow; i += 32) {
+        const int m = m0 + i / kLinesPerRow, n = n0 + (i % kLinesPerRow) * kLineElts;
+        if (m < g.M && n < g.N) prefetch_l2(base + ((c_r + m) * g.ldadd + c_c + n) * (OUT_F32 ? 4 : 2));
+      }
+    };
+    prefetch_add(first_tile);
     int it = 0;
     for (int tile = first_tile; tile < g.total_tiles; tile += tile_stride, ++it) {
+      prefetch_add(tile + tile_stride);
       const int z = tile / tiles_per_z;
       const int rem = tile - z * tiles_per_z;
       const int m_blk = rem / g.n_tiles;

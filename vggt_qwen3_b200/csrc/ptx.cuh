@@ -87,7 +87,15 @@ __device__ __forceinline__ void mbar_wait_trap(uint32_t bar, uint32_t parity) {
 #if VQ_HANG_GUARD
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef VQ_TRAP_PRINT
+    if (++spins > (1u << 20)) {
+      printf("vq: mbarrier timeout block=(%d,%d,%d) thread=%d bar=0x%x parity=%u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+#else
     if (++spins > (1u << 24)) __trap();
+#endif
   }
 #else
   while (!mbar_try_wait(bar, parity)) {
@@ -330,6 +338,9 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

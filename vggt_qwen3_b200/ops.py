@@ -117,6 +117,11 @@ def attention_fwd(qkv: torch.Tensor, n_seq: int, seq_len: int, heads: int,
     return out
 
 
+def attention_tune(q_tiles_per_cta: int = -1, emu_pairs: int = -1) -> None:
+    """Force an attention kernel variant (tests / tuning); -1 keeps the current setting, q_tiles_per_cta=0 = auto."""
+    _lib.check(_lib.lib().vq_attention_tune(q_tiles_per_cta, emu_pairs), "vq_attention_tune")
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
               out_dtype: torch.dtype = torch.bfloat16, return_stats: bool = False):
     """Row LayerNorm of a 2-D f32/bf16 tensor (D % 128 == 0)."""
