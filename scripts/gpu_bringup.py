@@ -184,6 +184,9 @@ CASES = {
     "attn_frame32": lambda: case_attn(32, 1374, 16, timing=True),
     "attn_global8": lambda: case_attn(1, 8 * 1374, 16, timing=True),
     "attn_global8x4": lambda: case_attn(4, 8 * 1374, 16, timing=True),
+    # model-like score magnitudes (LayerNorm-ed q, k: |s| of a few units)
+    "attn_frame32_m": lambda: case_attn(32, 1374, 16, timing=True, qscale=0.25),
+    "attn_global8x4_m": lambda: case_attn(4, 8 * 1374, 16, timing=True, qscale=0.25),
 }
 
 

@@ -32,10 +32,10 @@ def _restore_variant():
     from vggt_qwen3_b200 import ops
 
     yield
-    ops.attention_tune(0, 2)
+    ops.attention_tune(0, 3)
 
 
-@pytest.mark.parametrize("qt", [1, 2])
+@pytest.mark.parametrize("qt", [1, 2, 3, 4])
 @pytest.mark.parametrize("n_seq,L,heads,qscale", [
     (1, 128, 1, 2.0), (2, 64, 2, 2.0), (2, 65, 2, 2.0), (3, 50, 1, 2.0), (2, 129, 1, 2.0), (2, 200, 2, 2.0),
     (2, 300, 3, 2.0), (2, 1374, 2, 12.0), (1, 2000, 2, 0.05), (1, 2 * 1374, 4, 2.0), (1, 1, 1, 2.0), (1, 257, 2, 4.0),
@@ -54,7 +54,7 @@ def test_attention_matches_fp32_reference(qt, n_seq, L, heads, qscale):
     _check(out, _reference(qkv, n_seq, L, heads))
 
 
-@pytest.mark.parametrize("emu", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("emu", [0, 1, 2, 3, 4, 5, 6])
 def test_attention_exp2_emulation_share(emu):
     """Every split between MUFU.EX2 and the FMA-pipe polynomial stays within the tolerance."""
     from vggt_qwen3_b200 import ops
@@ -80,7 +80,7 @@ def test_attention_growing_maximum():
     k = torch.randn(L, 64, device="cuda", generator=g).abs() * torch.linspace(0.1, 4.0, L, device="cuda")[:, None]
     v = torch.randn(L, 64, device="cuda", generator=g)
     qkv = torch.cat([q, k, v], dim=1).bfloat16()
-    for qt in (1, 2):
+    for qt in (1, 2, 3, 4):
         ops.attention_tune(qt, 2)
         out = ops.attention_fwd(qkv, n_seq, L, heads)
         torch.cuda.synchronize()

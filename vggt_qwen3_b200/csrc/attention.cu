@@ -130,12 +130,12 @@ __device__ __forceinline__ float2 exp2_emulated(float2 x) {
 
 // p[32] (packed bf16 pairs) = exp2(s[64] - m); returns the row sum of the fp32 values.
 // EMU of every 8 pairs go through exp2_emulated, the rest through MUFU.EX2.
-template <int EMU, int DBG = 0>
-__device__ __forceinline__ float exp_row(const float (&s)[64], float m, uint32_t (&p)[32]) {
+template <int EMU, int DBG = 0, int N = 64>
+__device__ __forceinline__ float exp_row(const float (&s)[N], float m, uint32_t (&p)[N / 2]) {
   const float2 neg_m = splat(-m);
   float2 acc0 = splat(0.f), acc1 = splat(0.f);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < N / 2; ++i) {
     const float2 x = add2(make_float2(s[2 * i], s[2 * i + 1]), neg_m);
     float2 e;
     if ((i & 7) < EMU) {
@@ -335,6 +335,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
             tmem_ld32(tS, r0);
             tmem_ld32(tS + 32, r1);
             tmem_wait_ld();
+            if constexpr (DBG & 32) {  // timing experiment: read S from TMEM three times (TMEM read bandwidth probe)
+              uint32_t d0[32], d1[32];
+#pragma unroll
+              for (int rpt = 0; rpt < 2; ++rpt) {
+                tmem_ld32(tS, d0);
+                tmem_ld32(tS + 32, d1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) asm volatile("" ::"r"(d0[i]), "r"(d1[i]));
+              }
+            }
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -465,6 +476,362 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
   }
 }
 
+
+// =====================================================================================================================
+// "Wide" variant: one flash-attention stream per 128-row query tile, 128 keys per step.
+//
+//   TMEM, per query tile t (256 columns):  S_t [+0, +128)    scores (fp32), one 128 x 128 x 64 SS MMA per step
+//                                           O_t [+128, +192)  output accumulator
+//                                           P_t [+192, +256)  bf16 probabilities (128 keys in 64 columns) = A of PV
+//   P has its own columns, so S_t(j+1) does not have to wait for P_t(j) V_j: the issuing warp launches S_t(j+1) the
+//   moment the softmax threads have pulled S_t(j) into registers (bar_sfree), and the exponentials of step j overlap
+//   the next score MMA.  The 128-key score MMA also halves the shared-memory operand traffic per key compared to two
+//   64-key MMAs (Q is re-read once per 128 keys instead of once per 64).
+//
+//   QT = 2: 256 query rows per CTA, one CTA per SM, 384 threads, 4-stage K/V ring (long sequences);
+//   QT = 1: 128 query rows per CTA, TWO CTAs per SM (256 TMEM columns, half the registers and smem each), 256
+//           threads, 3-stage ring: finer query granularity for ragged lengths, and the fill / drain of one CTA
+//           overlaps the steady state of its neighbour (frame attention, L = 1374).
+//   warps 0..4QT-1  softmax (tile = warp / 4, TMEM lane quarter = warp % 4): one thread per query row
+//   warp 4QT        TMA producer;   warps 4QT+1 .. 4QT+QT  MMA issuers (one per query tile);   the rest idle
+//
+// What bounds the softmax warps is the DISPATCH port, not a single pipe (scratch/ubench/pipes.cu: FADD2 / FFMA2 /
+// FMNMX3 / F2FP each hold dispatch for 2 clocks per warp instruction, MUFU.EX2 for 1 but its pipe for 8): a score
+// that goes through MUFU costs sub + max + ex2 + sum + cvt = 5 dispatch clocks and 8 MUFU clocks, an emulated one
+// ~14 dispatch clocks.  So besides moving a share of the exponentials to the FMA pipe, the kernel removes work per
+// score on the common path:
+//  * FAST PATH (warp-uniform, taken when every |score| of the step is <= kFastBound and every row's reference is still
+//    0): P = 2^s with NO max subtraction and no clamp.  bf16 / fp32 carry 2^+-64 exactly as well as values near 1,
+//    and O / l normalises at the end, so nothing is lost; the pass that would compute the row maximum computes
+//    max |s| instead and doubles as the range check.  With LayerNorm-ed q and k (|s| <= 11.6 |w_q| |w_k|) the model
+//    never leaves this path; any input that does falls back, per step, to
+//  * GENERAL PATH: true row maximum, lazy rescale (the reference only moves when the maximum outgrows it by 2^8),
+//    clamped emulation -- exactly the split-KV kernel's arithmetic.
+// =====================================================================================================================
+constexpr float kFastBound = 64.0f;
+
+template <int QT>
+struct AttnWideCfg {
+  static constexpr int kSoftmaxWarps = 4 * QT;
+  static constexpr int kTmaWarp = 4 * QT;
+  static constexpr int kMmaWarp = 4 * QT + 1;
+  static constexpr int kThreads = (4 * QT + 4) * 32;     // QT = 2: 384, QT = 1: 256
+  static constexpr int kStages = QT == 2 ? 4 : 3;
+  static constexpr int kMinBlocks = QT == 2 ? 1 : 2;
+  static constexpr int kTmemCols = 256 * QT;
+  // setmaxnreg moves registers inside the CTA's launch-time allocation: 384 x 168 >= 256 x 216 + 128 x 56 (QT = 2),
+  // 256 x 128 >= 128 x 216 + 128 x 40 (QT = 1)
+  static constexpr int kRegsSoftmax = 216;
+  static constexpr int kRegsLow = QT == 2 ? 56 : 40;
+  static constexpr int kNeeded = QT * kTileBytes + 2 * kStages * kTileBytes + 256;
+  static constexpr int kSmemBytes = QT == 2 ? kNeeded + 1024 : 115712;   // QT = 1: (228 KB - 2 KB) / 2 per CTA
+  static_assert(kNeeded <= kSmemBytes, "smem carve-up");
+};
+
+// p[N/2] (packed bf16 pairs) = exp2(s[N]) with NO reference subtraction and no clamp (callers guarantee
+// |s| <= kFastBound); returns the row sum.  EMU of every 8 pairs on the FMA pipe.
+template <int EMU, int N>
+__device__ __forceinline__ float exp_row_fast(const float (&s)[N], uint32_t (&p)[N / 2]) {
+  float2 acc0 = splat(0.f), acc1 = splat(0.f);
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const float2 x = make_float2(s[2 * i], s[2 * i + 1]);
+    float2 e;
+    if ((i & 7) < EMU) {
+      const float2 xr = add2(x, splat(12582912.0f));   // 1.5 * 2^23: the low mantissa bits now hold n = rint(x)
+      const float2 n = add2(xr, splat(-12582912.0f));
+      const float2 f = fma2(n, splat(-1.0f), x);
+      float2 q = splat(5.517166853e-02f);
+      q = fma2(q, f, splat(2.426111400e-01f));
+      q = fma2(q, f, splat(6.932609677e-01f));
+      q = fma2(q, f, splat(9.999280572e-01f));
+      e.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(xr.x) << 23));
+      e.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(xr.y) << 23));
+    } else {
+      e.x = ex2_approx(x.x);
+      e.y = ex2_approx(x.y);
+    }
+    if (i & 1) acc1 = add2(acc1, e);
+    else acc0 = add2(acc0, e);
+    p[i] = pack_bf16x2(e.x, e.y);
+  }
+  const float2 a = add2(acc0, acc1);
+  return a.x + a.y;
+}
+
+template <int QT, int EMU>
+__global__ void __launch_bounds__(AttnWideCfg<QT>::kThreads, AttnWideCfg<QT>::kMinBlocks)
+attention_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g) {
+  using Cfg = AttnWideCfg<QT>;
+  constexpr int kKVStages = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (smem_base - smem_u32(smem_raw) + Cfg::kNeeded > Cfg::kSmemBytes) __trap();  // carve-up does not fit
+  const uint32_t smem_q = smem_base;                               // QT tiles
+  const uint32_t smem_k = smem_base + QT * kTileBytes;             // kKVStages tiles
+  const uint32_t smem_v = smem_k + kKVStages * kTileBytes;         // kKVStages tiles
+  const uint32_t bar_base = smem_v + kKVStages * kTileBytes;
+  const uint32_t bar_qfull = bar_base;
+  const uint32_t bar_kfull = bar_base + 8;
+  const uint32_t bar_vfull = bar_kfull + 8 * kKVStages;
+  const uint32_t bar_kvempty = bar_vfull + 8 * kKVStages;
+  const uint32_t bar_sfull = bar_kvempty + 8 * kKVStages;  // [2] S_t(j) is in TMEM
+  const uint32_t bar_sfree = bar_sfull + 16;               // [2] S_t(j) has been read into registers
+  const uint32_t bar_pfull = bar_sfree + 16;               // [2] P_t(j) is in TMEM (and O_t rescaled if needed)
+  const uint32_t bar_pvdone = bar_pfull + 16;              // [2] P_t(j) V_j has retired: P_t free, O_t stable
+  const uint32_t tmem_slot = bar_pvdone + 16;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;   // q-block fastest: K / V stay in L2
+  const int L = g.seq_len;
+  const int HD = g.heads * kHeadDim;
+  const int seq_row0 = seq * L;
+  const int q_row0 = qb * QT * kTileQ;
+  const int n_qtiles = (QT == 2 && q_row0 + kTileQ < L) ? 2 : 1;
+  const int n_kv = g.n_kv_tiles;
+
+  if (warp == Cfg::kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(bar_qfull, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(bar_kfull + 8 * s, 1);
+      mbar_init(bar_vfull + 8 * s, 1);
+      mbar_init(bar_kvempty + 8 * s, n_qtiles);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_sfull + 8 * t, 1);
+      mbar_init(bar_sfree + 8 * t, 4);
+      mbar_init(bar_pfull + 8 * t, 4);
+      mbar_init(bar_pvdone + 8 * t, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == Cfg::kMmaWarp) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp >= Cfg::kTmaWarp) {
+    setmaxnreg_dec<Cfg::kRegsLow>();
+    if (warp == Cfg::kTmaWarp) {
+      if (lane == 0) {
+        // ===================== TMA producer =====================
+        mbar_arrive_expect_tx(bar_qfull, n_qtiles * kTileBytes);
+        for (int t = 0; t < n_qtiles; ++t)
+          tma_load_2d(smem_q + t * kTileBytes, &tmQKV, bar_qfull, head * kHeadDim, seq_row0 + q_row0 + t * kTileQ);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < n_kv; ++j) {
+          mbar_wait(bar_kvempty + 8 * stage, phase ^ 1);
+          const int row = seq_row0 + j * kTileKV;
+          mbar_arrive_expect_tx(bar_kfull + 8 * stage, kTileBytes);
+          tma_load_2d(smem_k + stage * kTileBytes, &tmQKV, bar_kfull + 8 * stage, HD + head * kHeadDim, row);
+          mbar_arrive_expect_tx(bar_vfull + 8 * stage, kTileBytes);
+          tma_load_2d(smem_v + stage * kTileBytes, &tmQKV, bar_vfull + 8 * stage, 2 * HD + head * kHeadDim, row);
+          if (++stage == kKVStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp - Cfg::kMmaWarp < n_qtiles) {
+      // ===================== MMA issuer of query tile t =====================
+      const int t = warp - Cfg::kMmaWarp;
+      const uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(kTileQ, kHeadDim, 0, 1);  // V is MN-major (d contiguous)
+      const uint64_t desc_q = make_smem_desc(smem_q + t * kTileBytes, 16, 1024);
+      const uint64_t desc_k = make_smem_desc(smem_k, 16, 1024);
+      const uint64_t desc_v = make_smem_desc(smem_v, 8192, 1024);
+      const uint32_t tS = tmem_base + t * 256, tO = tS + 128, tP = tS + 192;
+      auto issue_s = [&](int stage) {
+        if (elect_one()) {
+          const uint64_t b0 = desc_k + (uint64_t)(stage * (kTileBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            umma_ss(tS, desc_q + (uint64_t)(k * 2), b0 + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+          umma_commit(bar_sfull + 8 * t);
+        }
+        __syncwarp();
+      };
+      mbar_wait(bar_qfull, 0);
+      mbar_wait(bar_kfull, 0);
+      tc_fence_after();
+      issue_s(0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        const int nstage = (stage + 1 == kKVStages) ? 0 : stage + 1;
+        const uint32_t nphase = (stage + 1 == kKVStages) ? (phase ^ 1) : phase;
+        if (j + 1 < n_kv) {
+          mbar_wait_fast(bar_kfull + 8 * nstage, nphase);
+          mbar_wait_fast(bar_sfree + 8 * t, j & 1);     // S_t(j) is in registers: its columns may be overwritten
+          tc_fence_after();
+          issue_s(nstage);
+        }
+        mbar_wait_fast(bar_vfull + 8 * stage, phase);
+        mbar_wait_fast(bar_pfull + 8 * t, j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          // 16 keys per MMA: 8 TMEM columns of packed bf16 P, 16 smem rows (2048 B = 128 descriptor units) of V
+          const uint64_t b0 = desc_v + (uint64_t)(stage * (kTileBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < kTileKV / 16; ++k)
+            umma_ts(tO, tP + k * 8, b0 + (uint64_t)(k * 128), idesc_o, (j | k) ? 1u : 0u);
+          umma_commit(bar_pvdone + 8 * t);
+          umma_commit(bar_kvempty + 8 * stage);
+        }
+        __syncwarp();
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ===================== softmax warps =====================
+    setmaxnreg_inc<Cfg::kRegsSoftmax>();
+    const int t = warp >> 2;
+    if (t < n_qtiles) {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+      const uint32_t tS = tmem_base + lane_addr + t * 256;
+      const uint32_t tO = tS + 128;
+      const uint32_t tP = tS + 192;
+      float m_ref = 0.f, l_run = 0.f;
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait_trap(bar_sfull + 8 * t, j & 1);
+        tc_fence_after();
+        float s[128];
+        {
+          uint32_t r[4][32];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, r[c]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[c][i]);
+        }
+        // hand the S columns back to the tensor core: S_t(j+1) overlaps this step's exponentials
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sfree + 8 * t);
+
+        const int n_valid = L - j * kTileKV;   // keys of this tile inside the sequence
+        const bool tail = n_valid < kTileKV;
+        // one pass: max |s| (the range check of the fast path)
+        float ma0 = fmaxf(fabsf(s[0]), fabsf(s[1])), ma1 = fmaxf(fabsf(s[2]), fabsf(s[3]));
+#pragma unroll
+        for (int i = 4; i < 128; i += 4) {
+          ma0 = fmaxf(fmaxf(ma0, fabsf(s[i])), fabsf(s[i + 1]));
+          ma1 = fmaxf(fmaxf(ma1, fabsf(s[i + 2])), fabsf(s[i + 3]));
+        }
+        // NaN-safe: !(x <= bound) is true for NaN, which then takes the general path like any other outlier
+        const bool outlier = !(fmaxf(ma0, ma1) <= kFastBound) || m_ref != 0.f;
+        uint32_t p[64];
+        float alpha = 1.f;
+        bool rescale = false;
+        if (!tail && !__any_sync(0xffffffffu, outlier)) {
+          l_run += exp_row_fast<EMU, 128>(s, p);
+        } else {
+          if (tail) {
+#pragma unroll
+            for (int i = 0; i < 128; ++i)
+              if (i >= n_valid) s[i] = -INFINITY;
+          }
+          float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+#pragma unroll
+          for (int i = 4; i < 128; i += 4) {
+            mx0 = fmaxf(fmaxf(mx0, s[i]), s[i + 1]);
+            mx1 = fmaxf(fmaxf(mx1, s[i + 2]), s[i + 3]);
+          }
+          const float mx = fmaxf(mx0, mx1);
+          if (j == 0) {
+            // rows whose scores are in range keep the reference 0 (so that later steps can take the fast path);
+            // an entirely masked first tile (mx = -inf) as well: P = 0, l stays 0
+            m_ref = (mx == -INFINITY || fabsf(mx) <= kFastBound) ? 0.f : mx;
+          } else {
+            // lazy rescale: the reference only moves when the row maximum outgrows it by more than 2^8
+            // (a reference of 0 additionally tolerates everything up to kFastBound)
+            const bool grow = mx > m_ref + kRescaleThreshold && !(m_ref == 0.f && mx <= kFastBound);
+            rescale = __any_sync(0xffffffffu, grow);
+            if (rescale) {
+              const float m_new = grow ? mx : m_ref;
+              alpha = ex2_approx(m_ref - m_new);
+              m_ref = m_new;
+              l_run *= alpha;
+            }
+          }
+          // all-MUFU: ex2(-inf) is exactly 0 for masked keys, and very negative scores need no clamp
+          l_run += exp_row<0, 0, 128>(s, m_ref, p);
+        }
+        if (j > 0) {
+          // P_t(j-1) V has retired: the P columns are free and O_t is not being accumulated into
+          mbar_wait_trap(bar_pvdone + 8 * t, (j - 1) & 1);
+          tc_fence_after();
+          if (rescale) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tO + c * 16, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + c * 16, o);
+            }
+          }
+        }
+        {
+          uint32_t (&p0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&p[0]);
+          uint32_t (&p1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&p[32]);
+          tmem_st32(tP, p0);
+          tmem_st32(tP + 32, p1);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pfull + 8 * t);
+      }
+
+      // ---- O / l -> bf16 -> out[row, head*64 .. +64]
+      mbar_wait_trap(bar_pvdone + 8 * t, (n_kv - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      const int q_in_seq = q_row0 + t * kTileQ + row;
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) +
+                           (long long)(seq_row0 + q_in_seq) * HD + head * kHeadDim;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_wait_ld();
+        if (q_in_seq < L) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + c * 32 + i) = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == Cfg::kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 }  // namespace vq
 
 namespace vq {
@@ -474,15 +841,16 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
   return v < lo ? lo : v > hi ? hi : v;
 }
 // pairs (of every 8) whose exponentials run on the FMA pipe instead of the MUFU
-static int g_attn_emu = env_int("VQ_ATTN_EMU", 2, 0, 4);
-// query tiles per CTA: 0 = by sequence length (1 up to kShortSeq keys, 2 above); 1 / 2 force a variant
-static int g_attn_qt = env_int("VQ_ATTN_QT", 0, 0, 2);
-static int g_attn_dbg = env_int("VQ_ATTN_DBG", 0, 0, 31);  // timing experiments only (results are wrong when non-zero)
+static int g_attn_emu = env_int("VQ_ATTN_EMU", 3, 0, 6);
+// kernel variant: 0 = automatic; 1 / 2 = split-KV kernel with 1 / 2 query tiles per CTA; 3 / 4 = wide kernel with
+// 2 / 1 query tiles per CTA
+static int g_attn_qt = env_int("VQ_ATTN_QT", 0, 0, 4);
+static int g_attn_dbg = env_int("VQ_ATTN_DBG", 0, 0, 63);  // timing experiments only (results are wrong when non-zero)
 }  // namespace vq
 
 extern "C" int vq_attention_tune(int32_t q_tiles_per_cta, int32_t emu_pairs) {
-  if (q_tiles_per_cta >= 0) vq::g_attn_qt = q_tiles_per_cta > 2 ? 2 : q_tiles_per_cta;
-  if (emu_pairs >= 0) vq::g_attn_emu = emu_pairs > 4 ? 4 : emu_pairs;
+  if (q_tiles_per_cta >= 0) vq::g_attn_qt = q_tiles_per_cta > 4 ? 4 : q_tiles_per_cta;
+  if (emu_pairs >= 0) vq::g_attn_emu = emu_pairs > 6 ? 6 : emu_pairs;
   return VQ_OK;
 }
 
@@ -501,16 +869,31 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
   if (!tm) return VQ_ERR_CUDA;
 
   const int emu = g_attn_emu;
+  const int emu4 = emu > 4 ? 4 : emu;   // the split-KV kernels are instantiated for 0..4
   const int dbg = g_attn_dbg;
   const int force_qt = g_attn_qt;
   constexpr int kShortSeq = 4096;
-  const int qt = (force_qt == 1 || force_qt == 2) ? force_qt : (seq_len <= kShortSeq ? 1 : 2);
+  // default: the wide kernel; one query tile per CTA and two CTAs per SM up to kLongSeq keys (frame attention and
+  // 8-frame global attention), two query tiles per CTA beyond (32-frame global attention: measured 2 % faster there)
+  (void)kShortSeq;
+  constexpr int kLongSeq = 16384;
+  const int qt = (force_qt >= 1 && force_qt <= 4) ? force_qt : (seq_len <= kLongSeq ? 4 : 3);
 
   using Kern = void (*)(const CUtensorMap, const AttnArgs);
   Kern kern = nullptr;
-  if (qt == 2) {
-    kern = emu == 0 ? attention_fwd_kernel<2, 0, 0> : emu == 1 ? attention_fwd_kernel<2, 1, 0>
-         : emu == 2 ? attention_fwd_kernel<2, 2, 0> : emu == 3 ? attention_fwd_kernel<2, 3, 0>
+  if (qt == 4) {
+    kern = emu == 0 ? attention_fwd_wide_kernel<1, 0> : emu == 1 ? attention_fwd_wide_kernel<1, 1>
+         : emu == 2 ? attention_fwd_wide_kernel<1, 2> : emu == 3 ? attention_fwd_wide_kernel<1, 3>
+         : emu == 4 ? attention_fwd_wide_kernel<1, 4> : emu == 5 ? attention_fwd_wide_kernel<1, 5>
+                                                                : attention_fwd_wide_kernel<1, 6>;
+  } else if (qt == 3) {
+    kern = emu == 0 ? attention_fwd_wide_kernel<2, 0> : emu == 1 ? attention_fwd_wide_kernel<2, 1>
+         : emu == 2 ? attention_fwd_wide_kernel<2, 2> : emu == 3 ? attention_fwd_wide_kernel<2, 3>
+         : emu == 4 ? attention_fwd_wide_kernel<2, 4> : emu == 5 ? attention_fwd_wide_kernel<2, 5>
+                                                                : attention_fwd_wide_kernel<2, 6>;
+  } else if (qt == 2) {
+    kern = emu4 == 0 ? attention_fwd_kernel<2, 0, 0> : emu4 == 1 ? attention_fwd_kernel<2, 1, 0>
+         : emu4 == 2 ? attention_fwd_kernel<2, 2, 0> : emu4 == 3 ? attention_fwd_kernel<2, 3, 0>
                                                                 : attention_fwd_kernel<2, 4, 0>;
     switch (dbg) {
       case 1: kern = attention_fwd_kernel<2, 0, 1>; break;
@@ -518,16 +901,21 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
       case 4: kern = attention_fwd_kernel<2, 0, 4>; break;
       case 8: kern = attention_fwd_kernel<2, 0, 8>; break;
       case 16: kern = attention_fwd_kernel<2, 0, 16>; break;
+      case 32: kern = attention_fwd_kernel<2, 0, 32>; break;
+      case 40: kern = attention_fwd_kernel<2, 0, 40>; break;
+      case 41: kern = attention_fwd_kernel<2, 0, 41>; break;
+      case 9: kern = attention_fwd_kernel<2, 0, 9>; break;
       default: break;
     }
   } else {
-    kern = emu == 0 ? attention_fwd_kernel<1, 0, 0> : emu == 1 ? attention_fwd_kernel<1, 1, 0>
-         : emu == 2 ? attention_fwd_kernel<1, 2, 0> : emu == 3 ? attention_fwd_kernel<1, 3, 0>
+    kern = emu4 == 0 ? attention_fwd_kernel<1, 0, 0> : emu4 == 1 ? attention_fwd_kernel<1, 1, 0>
+         : emu4 == 2 ? attention_fwd_kernel<1, 2, 0> : emu4 == 3 ? attention_fwd_kernel<1, 3, 0>
                                                                 : attention_fwd_kernel<1, 4, 0>;
   }
-  const int smem_bytes = qt == 2 ? AttnCfg<2>::kSmemBytes : AttnCfg<1>::kSmemBytes;
-  const int threads = qt == 2 ? AttnCfg<2>::kThreads : AttnCfg<1>::kThreads;
-  static bool configured[3][5] = {};
+  const int smem_bytes = qt == 4 ? AttnWideCfg<1>::kSmemBytes : qt == 3 ? AttnWideCfg<2>::kSmemBytes : qt == 2 ? AttnCfg<2>::kSmemBytes : AttnCfg<1>::kSmemBytes;
+  const int threads = qt == 4 ? AttnWideCfg<1>::kThreads : qt == 3 ? AttnWideCfg<2>::kThreads : qt == 2 ? AttnCfg<2>::kThreads : AttnCfg<1>::kThreads;
+  const int q_tiles = (qt == 1 || qt == 4) ? 1 : 2;
+  static bool configured[5][7] = {};
   if (!configured[qt][emu] || dbg) {
     VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -539,7 +927,7 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
   g.seq_len = seq_len;
   g.heads = heads;
   g.n_kv_tiles = (seq_len + kTileKV - 1) / kTileKV;
-  dim3 grid((seq_len + qt * kTileQ - 1) / (qt * kTileQ), heads, n_seq);
+  dim3 grid((seq_len + q_tiles * kTileQ - 1) / (q_tiles * kTileQ), heads, n_seq);
   {
     const double flops = 4.0 * n_seq * heads * (double)seq_len * seq_len * kHeadDim;
     const double bytes = 2.0 * (double)rows * HD * 4.0;  // q, k, v read once + out written (bf16)

@@ -35,8 +35,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// VQ_MBAR_HINT_NS: suspend-time hint of try_wait.  The hardware parks the warp until the phase completes or the
+// hint expires, so a waiting warp issues one instruction per hint period instead of spinning through the default
+// (much shorter) time slice: fewer issue slots and less power taken from the warps that do the work.
+#ifndef VQ_MBAR_HINT_NS
+#define VQ_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if VQ_MBAR_HINT_NS > 0
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"((uint32_t)VQ_MBAR_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -46,6 +63,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // True in exactly one (elected) lane of a fully converged warp.  Used to predicate only the tcgen05 / TMA issue
