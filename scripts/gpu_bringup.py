@@ -98,6 +98,54 @@ def case_gemm(M, N, K, a_major=0, b_major=0, epi="linear", out_f32=False, timing
     return ok, msg
 
 
+def case_qkv_rope(frames, grid, heads, timing=False):
+    """QKV GEMM with the fused per-head QK LayerNorm + 2-D RoPE + q pre-scale epilogue against torch fp32."""
+    import torch
+
+    from oracle import aggregator_ref as A
+    from vggt_qwen3_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    D, P = heads * 64, 5 + grid * grid
+    M = frames * P
+    x = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(3 * D, D, device="cuda", generator=g) / math.sqrt(D)).bfloat16()
+    bias = torch.randn(3 * D, device="cuda", generator=g) * 0.1
+    qn_w, kn_w = (torch.rand(64, device="cuda", generator=g) + 0.5 for _ in range(2))
+    qn_b, kn_b = (torch.randn(64, device="cuda", generator=g) * 0.1 for _ in range(2))
+    cos, sin = (t.cuda().contiguous() for t in A.rope_tables(grid, 64))
+    q_scale = 1.4426950408889634 / 8.0
+    extra = dict(tokens_per_frame=P, patch_start=5, grid_w=grid, apply_qknorm_rope=1, qn_w=qn_w, qn_b=qn_b, kn_w=kn_w,
+                 kn_b=kn_b, qk_eps=1e-5, q_scale=q_scale, rope_cos=cos, rope_sin=sin, rope_positions=grid + 1)
+    out = ops.gemm(x, w, bias=bias, epilogue=ops.EPI_QKV_ROPE, extra=extra)
+    torch.cuda.synchronize()
+    qkv = (x.float() @ w.float().t() + bias).view(frames, P, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    q = torch.nn.functional.layer_norm(qkv[0], (64,), qn_w, qn_b, 1e-5)
+    k = torch.nn.functional.layer_norm(qkv[1], (64,), kn_w, kn_b, 1e-5)
+    pos = torch.zeros(P, 2, dtype=torch.long, device="cuda")
+    yy, xx = torch.meshgrid(torch.arange(grid, device="cuda"), torch.arange(grid, device="cuda"), indexing="ij")
+    pos[5:, 0], pos[5:, 1] = yy.flatten() + 1, xx.flatten() + 1
+    pos = pos[None].expand(frames, P, 2)
+    q = A.rope_2d(q, pos, cos, sin) * q_scale
+    k = A.rope_2d(k, pos, cos, sin)
+    ref = torch.stack([q, k, qkv[2]], 0).permute(1, 3, 0, 2, 4).reshape(M, 3 * D)
+    rel = _rel(out, ref)
+    msg = f"rel={rel:.3e} cos={_cos(out, ref):.6f}"
+    if timing:
+        for _ in range(3):
+            ops.gemm(x, w, bias=bias, epilogue=ops.EPI_QKV_ROPE, extra=extra, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 20
+        for _ in range(n):
+            ops.gemm(x, w, bias=bias, epilogue=ops.EPI_QKV_ROPE, extra=extra, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        msg += f" time={ms*1e3:.1f}us {2*M*3*D*D/ms/1e9:.1f}TF/s"
+    return rel < 1e-2, msg
+
+
 def case_attn(n_seq, L, heads, timing=False, qscale=2.0):
     import torch
 
@@ -169,6 +217,9 @@ CASES = {
     "gemm_t3_fc1": lambda: case_gemm(43968, 4096, 1024, epi="gelu", timing=True),
     "gemm_t3_fc2": lambda: case_gemm(43968, 1024, 4096, epi="lsres", out_f32=True, timing=True),
     "gemm_t3_proj": lambda: case_gemm(43968, 1024, 1024, epi="lsres", out_f32=True, timing=True),
+    "gemm_qkvrope_small": lambda: case_qkv_rope(3, 6, 2),
+    "gemm_t_qkvrope": lambda: case_qkv_rope(8, 37, 16, timing=True),
+    "gemm_t3_qkvrope": lambda: case_qkv_rope(32, 37, 16, timing=True),
     # --- attention
     "attn_128": lambda: case_attn(1, 128, 1),
     "attn_256": lambda: case_attn(1, 256, 2),

@@ -84,3 +84,13 @@ def test_gemm_gelu_backward():
     out = ops.gemm(A, B, epilogue=ops.EPI_GELU_BWD, aux=pre)
     torch.cuda.synchronize()
     assert _rel(out, ref * (cdf + x * pdf)) < 1e-2
+
+
+@pytest.mark.parametrize("frames,grid,heads", [(3, 6, 2), (2, 37, 4), (5, 9, 16)])
+def test_gemm_qkv_qknorm_rope_epilogue(frames, grid, heads):
+    """qkv projection with the fused per-head QK LayerNorm(64) + 2-D RoPE + q pre-scale ([UPSTREAM]
+    vggt/layers/attention.py q_norm / k_norm, vggt/layers/rope.py) against the oracle's rope_2d on torch fp32."""
+    from scripts.gpu_bringup import case_qkv_rope
+
+    ok, msg = case_qkv_rope(frames, grid, heads)
+    assert ok, msg

@@ -66,7 +66,8 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 / 512)
   // per-warp [bias|gamma] vectors (8 warps x BLOCK_N floats), then EITHER the QKV extras (q/k-norm affine 4 x 64 and
   // the rope cos/sin tables) OR the per-warp transposition buffers of the other epilogues
-  static constexpr int kQkvExtraBytes = 4 * 64 * 4 + 2 * kRopeSmemPos * 16 * 4;
+  static constexpr int kQkvStageWarpBytes = 32 * 128;   // one 32-row x 64-column bf16 head block per epilogue warp
+  static constexpr int kQkvExtraBytes = 4 * 64 * 4 + 2 * kRopeSmemPos * 16 * 4 + 8 * kQkvStageWarpBytes;
   static constexpr int kTransposeBytes = 8 * kStageWarpFloats * 4;
   static constexpr int kEpiVecBytes =
       8 * BLOCK_N * 4 + (kQkvExtraBytes > kTransposeBytes ? kQkvExtraBytes : kTransposeBytes);
@@ -192,6 +193,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* qk_vec = epi_vec + 8 * BLOCK_N;        // [q_w | q_b | k_w | k_b] x 64
   float* rope_vec = qk_vec + 4 * 64;            // [cos | sin] x kRopeSmemPos x 16
   float* stage_vec = epi_vec + 8 * BLOCK_N;     // aliases the QKV extras: 8 x [32][kStageLd] f32 transposition buffers
+  uint8_t* qkv_stage = reinterpret_cast<uint8_t*>(rope_vec + 2 * kRopeSmemPos * 16);   // 8 x 4 KB, after the rope tables
   const bool rope_in_smem = g.rope_positions > 0 && g.rope_positions <= kRopeSmemPos;
 
   const int warp = threadIdx.x >> 5;
@@ -483,10 +485,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] *= g.q_scale;
           }
-          if (row_ok) {
-            const long long off = (c_r + m) * g.ldc + c_c + n_head;
+          // One row per thread would make every store instruction touch 32 different lines (16 B each): go through
+          // a per-warp smem block (16-byte chunks XOR-swizzled by row, conflict-free both ways) and store 4 whole
+          // 128-byte row segments per instruction instead.
+          uint8_t* st = qkv_stage + warp * Cfg::kQkvStageWarpBytes;
+          __syncwarp();   // the previous head's read-back is complete
 #pragma unroll
-            for (int i = 0; i < 64; i += 8) store8_bf16(g.C, off + i, v + i);
+          for (int c = 0; c < 8; ++c) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
+            u.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+            u.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+            u.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+            *reinterpret_cast<uint4*>(st + lane * 128 + ((c ^ (lane & 7)) << 4)) = u;
+          }
+          __syncwarp();
+          {
+            const int cc = lane & 7, rsub = lane >> 3;
+            const int m_warp0 = m_blk * kTileM + (int)cta_rank * kBlockM + quarter * 32;
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const int r = ps * 4 + rsub;
+              const uint4 u = *reinterpret_cast<const uint4*>(st + r * 128 + ((cc ^ (r & 7)) << 4));
+              if (m_warp0 + r < g.M)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.C) +
+                                          (c_r + m_warp0 + r) * g.ldc + c_c + n_head + cc * 8) = u;
+            }
           }
         }
       } else {
@@ -699,6 +723,21 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
   if (force_cg == 1 || force_cg == 2) cg = (force_cg == 2 && (Z0 * Z1 != 1 || d->N < 256)) ? 1 : force_cg;
   const int m_tiles = (d->M + kBlockM * cg - 1) / (kBlockM * cg);
   int block_n = 256;
+  if (cg == 2 && d->N % 128 == 0 && d->K <= 1024) {
+    // Wave quantisation: a persistent grid of P pairs runs ceil(tiles / P) rounds.  256 x 128 tiles cost half a
+    // 256 x 256 tile plus ~8 % (A is re-read twice as often): take them when that is fewer tile-rounds overall
+    // (c2 proj: M = 10992, N = 1024 -> 172 tiles on 74 pairs = 3 rounds, against 5 half-rounds = 2.7).  Measured: a
+    // 5 % gain for K = 1024, a loss for K = 4096 (fc2), hence the K limit.
+    const long long pairs = (num_sms() > 1 ? num_sms() : 148) / 2;
+    const long long t256 = (long long)m_tiles * ((d->N + 255) / 256), t128 = (long long)m_tiles * (d->N / 128);
+    const double cost256 = (double)((t256 + pairs - 1) / pairs);
+    const double cost128 = (double)((t128 + pairs - 1) / pairs) * 0.54;
+    static const int force_bn = [] {
+      const char* e = getenv("VQ_GEMM_BLOCK_N");
+      return e ? atoi(e) : 0;
+    }();
+    if (force_bn == 128 || (force_bn == 0 && cost128 < cost256)) block_n = 128;
+  }
   if (cg == 1) {
     const long long tiles256 = (long long)m_tiles * ((d->N + 255) / 256) * Z0 * Z1;
     const int sms = num_sms() > 0 ? num_sms() : 148;
