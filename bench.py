@@ -63,6 +63,17 @@ def measured_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+def ncu_traffic(tag: str, m: int, n: int, k: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of the same kernel and shape (profiles/ncu_traffic.json, written by
+    scripts/ncu_summary.py from the round's .ncu-rep files); None when that shape was not captured."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None
+    rec = json.loads(p.read_text()).get(f"{tag}[{m}x{n}x{k}]")
+    return None if rec is None else rec
+
+
 # ------------------------------------------------------------------------------------------------ FLOP model
 def work_flops(wl: dict) -> dict:
     """Algorithmic FLOPs per step per GPU (2MNK per GEMM, 4 Nq Nkv D per attention, no pruning credit)."""
@@ -174,14 +185,21 @@ def run_b200(args) -> dict:
         reducer = BucketedGradAllReduce(grad_dtype=torch.bfloat16)
         finish_allreduce = attach_projector_allreduce(proj, reducer)
 
+    # N > 1: the gradient all-reduce of step i starts bucket by bucket inside the Perceiver backward and is awaited
+    # AFTER the frozen aggregator forward of step i+1 has been enqueued (that forward does not depend on the projector
+    # weights, so a trainer can run it ahead of the optimizer step); the last step's all-reduce is awaited by
+    # `drain()` inside the timed region.  Every step therefore contains one full all-reduce, as in the reference's DDP.
+    def drain():
+        finish_allreduce()
+        for p in proj.parameters():
+            p.grad = None
+
     def step_resident():
         tokens = agg.encode_tokens(images_dev, NUM_VIS_TOKENS)
         if bwd:
+            drain()                  # previous step's gradients are complete here (an optimizer step would follow)
             out = proj(tokens)
             out.backward(grad_out)
-            finish_allreduce()
-            for p in proj.parameters():
-                p.grad = None
         else:
             with torch.no_grad():
                 out = proj(tokens)
@@ -190,14 +208,13 @@ def run_b200(args) -> dict:
     def step_e2e():
         images_dev.copy_(images_host, non_blocking=True)                 # H2D of this step's inputs
         if bwd:
-            out = model.encode_images_trainable(images_dev)
+            tokens = model.encode_image_tokens(images_dev)
+            drain()
+            out = model.project_tokens(tokens)
             out.backward(grad_out)
-            finish_allreduce()
-            for p in proj.parameters():
-                p.grad = None
         else:
             out = model.encode_images(images_dev)
-        result_host.copy_(out.float().sum().reshape(1), non_blocking=True)  # D2H read of the step's result
+        result_host.copy_(out.detach().float().sum().reshape(1), non_blocking=True)  # D2H read of the step's result
         torch.cuda.current_stream().synchronize()
         return float(result_host[0])
 
@@ -215,6 +232,8 @@ def run_b200(args) -> dict:
         e0.record()
         for _ in range(steps):
             fn()
+        if bwd:
+            drain()   # the last step's all-reduce completes inside the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -235,11 +254,15 @@ def run_b200(args) -> dict:
     # ---- per-kernel roofline: instrumented repeat of the same steps (CUDA events around every launch, on the
     # launch stream); kept out of the timed region above so the events do not perturb `value`.
     roof, breakdown = None, {}
-    if rank == 0 and args.profile_steps > 0:
-        lib.vq_profile_enable(1)
+    # EVERY rank runs the instrumented steps (at N > 1 they contain the gradient all-reduce, a collective all ranks
+    # must enter); only rank 0 records and reports.
+    if args.profile_steps > 0:
+        if rank == 0:
+            lib.vq_profile_enable(1)
         for _ in range(args.profile_steps):
             step_resident()
-        torch.cuda.synchronize()
+        barrier()
+    if rank == 0 and args.profile_steps > 0:
         buf = ctypes.create_string_buffer(1 << 20)
         n = lib.vq_profile_dump(buf, len(buf))
         lib.vq_profile_enable(0)
@@ -277,6 +300,10 @@ def run_b200(args) -> dict:
                     "frac": round(ach / peaks["tf_sustained"], 4), "peak_source": peaks["src"] + " (sustained)",
                     "share_of_step": round(top["ms"] / total_ms, 4),
                     "avg_launch_us": round(1e3 * top["ms"] / top["launches"], 2), "traffic": None}
+            tr = ncu_traffic(top["tag"], top["m"], top["n"], top["k"])
+            if tr is not None:   # DRAM bytes per launch (read + write) from the committed ncu --set full capture
+                roof.update({"traffic": tr["bytes"], "traffic_unit": "bytes/launch", "traffic_source": tr["source"],
+                             "algorithmic_bytes": round(top["bytes"] / top["launches"])})
 
     out = {
         "metric": "encoded frames/sec (VGGT Aggregator + Perceiver projector)",
@@ -289,7 +316,8 @@ def run_b200(args) -> dict:
             "num_vis_tokens": NUM_VIS_TOKENS, "projector": "perceiver_small (4096/128 latents/8 heads/6 layers/16384)",
             "projector_backward": bwd, "dropout": "identity (eval-mode forward/backward)",
             "parallelism": f"dp{world} (scenes sharded, full replica per GPU" +
-                           (", bf16 Perceiver-grad all-reduce overlapped with backward)" if world > 1 and bwd else ")"),
+                           (", bf16 Perceiver-grad all-reduce overlapped with the backward and the next step's frozen aggregator "
+                            "forward)" if world > 1 and bwd else ")"),
             "l2": "per-step working set (4.3 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush",
         },
         "algorithmic_tflop_per_step_per_gpu": round(fl["total"] / 1e12, 3),
@@ -299,7 +327,8 @@ def run_b200(args) -> dict:
         "clocks": clocks,
         "e2e": {"value": round(frames / (ms_e2e / 1e3), 2), "unit": "frames/s", "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": images_host.numel() * 4, "d2h_bytes_per_step": 4,
-                "api": "VGGTQwen3VLM.encode_images_trainable + backward" if bwd else "VGGTQwen3VLM.encode_images"},
+                "api": "VGGTQwen3VLM.encode_image_tokens + project_tokens (= encode_images_trainable) + backward" if bwd
+                       else "VGGTQwen3VLM.encode_images"},
         "gpu_launches": int(launches) * args.steps,
         "gpu_launches_per_step": int(launches),
         "roofline": roof,

@@ -175,6 +175,25 @@ int vq_splice_overwrite(void* inputs_embeds, int32_t dtype, const int64_t* input
                         int32_t L, int32_t hidden, int32_t n_feat, int64_t image_id, int32_t* overflow_count,
                         vq_stream_t stream);
 
+/* f1: inference splice (src/inference/qa_inference.py:119-145, src/inference/arkit_inference.py:182-214).
+ * vq_find_first_token: *first (device int64, pre-set to n by the caller) = index of the first `token` in the
+ * flattened [B*L] ids, i.e. `(input_ids == id).nonzero()[0]`; left at n when absent.
+ * vq_splice_insert: with pos = *first % L, out_embeds[B, L-1+n_vis, hidden] = cat(emb[:, :pos], vis, emb[:, pos+1:])
+ * and out_mask likewise with ones over the inserted span (mask elements of 8, 4 or 1 bytes).  Writes nothing when
+ * *first == B*L (the reference returns its inputs unchanged).  No host synchronisation. */
+int vq_find_first_token(const int64_t* input_ids, int64_t n, int64_t token, int64_t* first, vq_stream_t stream);
+int vq_splice_insert(const void* inputs_embeds, int32_t dtype, const void* attention_mask, int32_t mask_elt_bytes,
+                     const void* vis_tokens, const int64_t* first_pos, void* out_embeds, void* out_mask, int32_t B,
+                     int32_t L, int32_t hidden, int32_t n_vis, vq_stream_t stream);
+
+/* f3: fused AdamW step for the projector parameter group (src/train/train_sft.py:138-163: torch.optim.AdamW, defaults
+ * betas (0.9, 0.999), eps 1e-8, decoupled weight decay).  One pass over HBM: reads p, m, v (f32) and the gradient
+ * (f32 or bf16, multiplied by grad_scale), writes p, m, v and, when param_bf16 is non-null, the bf16 compute copy of
+ * the updated weights that the forward GEMMs read.  `step` counts from 1 (bias correction).  n % 4 == 0. */
+int vq_adamw_step(float* param, float* exp_avg, float* exp_avg_sq, const void* grad, int32_t grad_dtype,
+                  void* param_bf16, int64_t n, int32_t step, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, float grad_scale, vq_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * vq_aggregator_forward — the whole frozen VGGT Aggregator forward (csrc/aggregator.cu): replaces
  * `self.vision_model.aggregator(images)` at src/models/vggt_qwen3_vlm.py:144 ([UPSTREAM] vggt/models/aggregator.py).

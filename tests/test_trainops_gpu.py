@@ -1,0 +1,113 @@
+"""GPU parity of the kernels either side of the encode path, through the C ABI:
+the inference splice against the oracle restatement of `_insert_vision_tokens` (bit-exact), the fused AdamW against
+`torch.optim.AdamW` on the same gradients."""
+import pytest
+import torch
+
+from oracle import perceiver_ref as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,L,n,hidden,where,dtype,mask_dtype", [
+    (1, 40, 128, 2560, 7, torch.float32, torch.int64), (1, 12, 16, 64, 0, torch.bfloat16, torch.int64),
+    (1, 12, 16, 64, 11, torch.float32, torch.bool), (2, 20, 8, 128, 25, torch.float32, torch.int32),
+    (1, 9, 4, 32, None, torch.float32, torch.int64),
+])
+def test_splice_insert_matches_reference_restatement(B, L, n, hidden, where, dtype, mask_dtype):
+    from vggt_qwen3_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, 50, (B, L), generator=g)
+    if where is not None:
+        ids.view(-1)[where] = 777
+        if where + 3 < B * L:
+            ids.view(-1)[where + 3] = 777      # a later <image> token must be ignored
+    emb = torch.randn(B, L, hidden, generator=g).to(dtype)
+    mask = (torch.rand(B, L, generator=g) > 0.2).to(mask_dtype)
+    vis = torch.randn(B, n, hidden, generator=g).to(dtype)
+    out, out_mask = ops.splice_insert(emb.cuda(), mask.cuda(), ids.cuda(), vis.cuda(), 777)
+    if where is None:
+        ref, ref_mask = emb, mask
+    else:
+        # the reference slices every sample at the position of the first hit (qa_inference.py:129-135)
+        pos = where % L
+        ref = torch.cat([emb[:, :pos], vis, emb[:, pos + 1:]], dim=1)
+        ref_mask = torch.cat([mask[:, :pos], torch.ones(B, n, dtype=mask_dtype), mask[:, pos + 1:]], dim=1)
+        if B == 1:
+            o_ref, o_mask = P.splice_insert(emb, mask, ids, vis, 777)
+            assert torch.equal(o_ref, ref) and torch.equal(o_mask, ref_mask)
+    assert out.shape == ref.shape and out_mask.shape == ref_mask.shape
+    assert torch.equal(out.cpu(), ref) and torch.equal(out_mask.cpu(), ref_mask)
+
+
+def test_fused_adamw_matches_torch_adamw():
+    from vggt_qwen3_b200.optim import FusedAdamW
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(257, 64), (4096,), (128, 512)]
+    ps_ref = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    ps = [torch.nn.Parameter(p.detach().clone()) for p in ps_ref]
+    kw = dict(lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    ref = torch.optim.AdamW(ps_ref, **kw)
+    opt = FusedAdamW(ps, **kw)
+    sched_ref = torch.optim.lr_scheduler.LambdaLR(ref, lambda s: 1.0 / (1 + s))
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0 / (1 + s))
+    for _ in range(5):
+        for a, b in zip(ps_ref, ps):
+            gr = torch.randn(a.shape, device="cuda", generator=g)
+            a.grad = gr.clone()
+            b.grad = gr
+        ref.step(); opt.step(); sched_ref.step(); sched.step()
+    for a, b in zip(ps_ref, ps):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), (a - b).abs().max()
+        sa, sb = ref.state[a], opt.state[b]
+        assert torch.allclose(sa["exp_avg"], sb["exp_avg"], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(sa["exp_avg_sq"], sb["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+
+
+def test_adamw_step_bf16_gradients_scale_and_compute_copy():
+    """The all-reduced gradient arrives in bf16 and unscaled (sum over ranks): grad_scale = 1/world folds the mean into
+    the update, and the bf16 compute copy of the new weights is written in the same pass."""
+    from vggt_qwen3_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n = 1 << 16
+    p = torch.randn(n, device="cuda", generator=g)
+    ref_p = torch.nn.Parameter(p.clone())
+    ref = torch.optim.AdamW([ref_p], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    copy = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    for step in range(1, 4):
+        gr = (torch.randn(n, device="cuda", generator=g) * 4).bfloat16()
+        ref_p.grad = gr.float() * 0.25
+        ref.step()
+        ops.adamw_step(p, m, v, gr, step, lr=1e-2, weight_decay=0.1, grad_scale=0.25, param_bf16=copy)
+    assert torch.allclose(p, ref_p.detach(), rtol=2e-5, atol=2e-6)
+    assert torch.equal(copy, p.bfloat16())
+
+
+def test_fused_adamw_refreshes_projector_compute_copies():
+    """After a fused step the projector's next forward uses the updated weights (bf16 copies written in the same pass,
+    f32 vector copies re-copied lazily): same result as stepping torch.optim.AdamW on an identical module."""
+    from vggt_qwen3_b200.optim import FusedAdamW
+    from vggt_qwen3_b200.projector_perceiver import PerceiverConfig, PerceiverProjector
+
+    cfg = PerceiverConfig(256, 64, 2, 2, 512, 0.0)
+    torch.manual_seed(0)
+    a = PerceiverProjector(cfg, in_dim=256, out_dim=192).cuda().eval()
+    b = PerceiverProjector(cfg, in_dim=256, out_dim=192).cuda().eval()
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(2, 64, 256, device="cuda").bfloat16()
+    go = torch.randn(2, 64, 192, device="cuda")
+    oa = torch.optim.AdamW(a.parameters(), lr=1e-2, weight_decay=0.01)
+    ob = FusedAdamW(b.parameters(), lr=1e-2, weight_decay=0.01).attach_projector(b)
+    for _ in range(2):
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad(set_to_none=True)
+            m(x).backward(go)
+            o.step()
+    ya, yb = a(x).float(), b(x).float()
+    assert torch.allclose(ya, yb, rtol=2e-2, atol=2e-2 * ya.abs().max().item())
+    for (n1, p1), (_, p2) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.allclose(p1, p2, rtol=1e-3, atol=1e-5), n1

@@ -173,6 +173,9 @@ _EXTRA_DECLS: dict[str, list] = {
     "vq_stem_finalize": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
     "vq_gather_tokens": [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp],
     "vq_splice_overwrite": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp],
+    "vq_find_first_token": [_vp, _i64, _i64, _vp, _vp],
+    "vq_splice_insert": [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "vq_adamw_step": [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp],
     "vq_softmax_fwd": [_vp, _vp, _i64, _i32, _i32, _i32, _vp],
     "vq_softmax_bwd": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp],
     "vq_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],

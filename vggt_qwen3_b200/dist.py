@@ -9,6 +9,7 @@ layers' backward GEMMs run.  Works with any torch.distributed backend (gloo on C
 """
 from __future__ import annotations
 
+import datetime
 import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -25,7 +26,10 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        # a bounded timeout turns a mismatched collective into an error instead of a silent hang
+        kw = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("VQ_DIST_TIMEOUT_S", "180"))), **kw)
     return rank, world, local
 
 

@@ -6,7 +6,7 @@ pointers to libvq_b200.so on the current stream and returns the output tensor.  
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 
@@ -174,3 +174,50 @@ def splice_overwrite(inputs_embeds: torch.Tensor, input_ids: torch.Tensor, featu
                                        _stream()),
         "vq_splice_overwrite")
     return inputs_embeds
+
+
+def splice_insert(inputs_embeds: torch.Tensor, attention_mask: torch.Tensor, input_ids: torch.Tensor,
+                  vis_tokens: torch.Tensor, image_id: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Inference splice (src/inference/qa_inference.py:119-145): the FIRST <image> token (in (batch, position) order)
+    is replaced in every sample by the vision tokens, the mask is extended with ones; inputs are returned unchanged
+    when there is no <image> token.  Two launches; the one 8-byte read-back replaces the reference's `.nonzero()`."""
+    if not inputs_embeds.is_cuda:
+        raise RuntimeError("splice_insert: CUDA tensors only")
+    B, L, Hd = inputs_embeds.shape
+    n = vis_tokens.shape[1]
+    emb = inputs_embeds.contiguous()
+    vis = vis_tokens.to(emb.dtype).contiguous()
+    mask = attention_mask.contiguous()
+    ids = input_ids.to(torch.int64).contiguous()
+    first = torch.full((1,), B * L, dtype=torch.int64, device=emb.device)
+    out = torch.empty((B, L - 1 + n, Hd), dtype=emb.dtype, device=emb.device)
+    out_mask = torch.empty((B, L - 1 + n), dtype=mask.dtype, device=emb.device)
+    _lib.check(_lib.lib().vq_find_first_token(ids.data_ptr(), B * L, image_id, first.data_ptr(), _stream()),
+               "vq_find_first_token")
+    _lib.check(
+        _lib.lib().vq_splice_insert(emb.data_ptr(), _dtype_code(emb.dtype), mask.data_ptr(), mask.element_size(),
+                                    vis.data_ptr(), first.data_ptr(), out.data_ptr(), out_mask.data_ptr(), B, L, Hd, n,
+                                    _stream()),
+        "vq_splice_insert")
+    if int(first.item()) >= B * L:
+        return inputs_embeds, attention_mask
+    return out, out_mask
+
+
+def adamw_step(param: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, grad: torch.Tensor, step: int, *,
+               lr: float, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+               grad_scale: float = 1.0, param_bf16: Optional[torch.Tensor] = None) -> None:
+    """In-place fused AdamW (torch.optim.AdamW semantics) on flat f32 param / state buffers; `grad` f32 or bf16."""
+    for t, name in ((param, "param"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, name)
+    n = param.numel()
+    assert exp_avg.numel() == n and exp_avg_sq.numel() == n and grad.numel() == n
+    assert param.is_contiguous() and exp_avg.is_contiguous() and exp_avg_sq.is_contiguous() and grad.is_contiguous()
+    if param_bf16 is not None:
+        _req(param_bf16, torch.bfloat16, "param_bf16")
+        assert param_bf16.numel() == n and param_bf16.is_contiguous()
+    _lib.check(
+        _lib.lib().vq_adamw_step(param.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), grad.data_ptr(),
+                                 _dtype_code(grad.dtype), param_bf16.data_ptr() if param_bf16 is not None else None, n,
+                                 step, lr, betas[0], betas[1], eps, weight_decay, grad_scale, _stream()),
+        "vq_adamw_step")

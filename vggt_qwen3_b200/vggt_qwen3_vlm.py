@@ -122,9 +122,18 @@ class VGGTQwen3VLM(nn.Module):
     def encode_images_trainable(self, images: torch.Tensor) -> torch.Tensor:
         """Same tokens, but the projector runs under autograd (the frozen aggregator stays under no_grad), so that
         stage-1 training actually reaches the Perceiver; the reference's `encode_images` cannot."""
-        with torch.no_grad():
-            agg = self._vision_tokens(images)
-        return self.projector(agg.to(dtype=self.projector.in_proj.weight.dtype))
+        return self.project_tokens(self.encode_image_tokens(images))
+
+    @torch.no_grad()
+    def encode_image_tokens(self, images: torch.Tensor) -> torch.Tensor:
+        """The frozen half of `encode_images_trainable` (reference :140-160): aggregator tokens [B, num_vis_tokens,
+        2048] in the projector's input dtype.  Independent of the projector weights, so a data-parallel trainer can
+        run it for step i+1 while the gradient all-reduce of step i is still in flight (bench.py does)."""
+        return self._vision_tokens(images).to(dtype=self.projector.in_proj.weight.dtype)
+
+    def project_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
+        """The trainable half (reference :162): `self.projector(tokens)` under autograd."""
+        return self.projector(tokens)
 
     def encode_geom(self, geom_token: Optional[Dict[str, torch.Tensor]]) -> Optional[torch.Tensor]:
         """[B, geom_tokens, hidden] from per-view (R 9 | t 3 | K 9 | depth_hist 16) features averaged over views
