@@ -134,7 +134,8 @@ def run_b200(args) -> dict:
     import torch.distributed as dist
 
     from vggt_qwen3_b200 import _lib
-    from vggt_qwen3_b200.dist import BucketedGradAllReduce, attach_projector_allreduce, init_from_env
+    from vggt_qwen3_b200.dist import (BucketedGradAllReduce, PeerCopyGradAllReduce, attach_projector_allreduce,
+                                      attach_projector_peer_allreduce, init_from_env)
     from vggt_qwen3_b200.projector_perceiver import PerceiverConfig
     from vggt_qwen3_b200.vggt_qwen3_vlm import VGGTQwen3VLM, VisionLanguageConfig
 
@@ -181,9 +182,22 @@ def run_b200(args) -> dict:
 
     reducer = None
     finish_allreduce = lambda: None
-    if world > 1 and bwd:
-        reducer = BucketedGradAllReduce(grad_dtype=torch.bfloat16)
-        finish_allreduce = attach_projector_allreduce(proj, reducer)
+    comm = "none"
+    if world > 1 and bwd and not os.environ.get("VQ_BENCH_NO_ALLREDUCE"):   # (debug switch: isolates comm cost)
+        mode = os.environ.get("VQ_ALLREDUCE", "peer")
+        if mode == "peer":
+            try:   # copy-engine reduce-scatter + all-gather over NVLink peer memory (no SMs taken from the GEMMs)
+                n_grad = sum(p.numel() for p in proj.parameters())
+                reducer = PeerCopyGradAllReduce(n_grad, dev)
+                finish_allreduce = attach_projector_peer_allreduce(proj, reducer)
+                comm = "bf16 Perceiver-grad all-reduce on the copy engines over NVLink peer memory (symmetric memory)"
+            except Exception as exc:   # symmetric memory unavailable on this box: NCCL
+                print(f"[bench] peer-copy all-reduce unavailable ({exc!r}); using NCCL", file=sys.stderr)
+                reducer = None
+        if reducer is None:
+            reducer = BucketedGradAllReduce(grad_dtype=torch.bfloat16, keep_wire=True)
+            finish_allreduce = attach_projector_allreduce(proj, reducer)
+            comm = "bf16 Perceiver-grad NCCL all-reduce, bucketed per layer"
 
     # N > 1: the gradient all-reduce of step i starts bucket by bucket inside the Perceiver backward and is awaited
     # AFTER the frozen aggregator forward of step i+1 has been enqueued (that forward does not depend on the projector
@@ -316,8 +330,8 @@ def run_b200(args) -> dict:
             "num_vis_tokens": NUM_VIS_TOKENS, "projector": "perceiver_small (4096/128 latents/8 heads/6 layers/16384)",
             "projector_backward": bwd, "dropout": "identity (eval-mode forward/backward)",
             "parallelism": f"dp{world} (scenes sharded, full replica per GPU" +
-                           (", bf16 Perceiver-grad all-reduce overlapped with the backward and the next step's frozen aggregator "
-                            "forward)" if world > 1 and bwd else ")"),
+                           (f", {comm}, overlapped with the next step's frozen aggregator forward; the reduced SUM stays "
+                            "bf16 for vq_adamw_step(grad_scale=1/N))" if world > 1 and bwd else ")"),
             "l2": "per-step working set (4.3 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush",
         },
         "algorithmic_tflop_per_step_per_gpu": round(fl["total"] / 1e12, 3),
@@ -334,6 +348,19 @@ def run_b200(args) -> dict:
         "roofline": roof,
         "kernel_breakdown": breakdown,
     }
+    if isinstance(reducer, PeerCopyGradAllReduce):
+        # self-check of the peer-memory all-reduce (outside the timed region): small integers are exact in bf16
+        idx = torch.arange(reducer.buf.numel(), device=dev) % 7 + 1
+        reducer.buf.copy_((idx * (rank + 1)).to(torch.bfloat16))
+        torch.cuda.synchronize()   # finish() runs on the reducer's stream; load() normally orders it after the producer
+        reducer._armed = True
+        reducer.finish()
+        torch.cuda.synchronize()
+        expect = (idx * (world * (world + 1) // 2)).to(torch.bfloat16)
+        ok = bool(torch.equal(reducer.buf, expect))
+        if not ok:
+            print("[bench] peer-memory all-reduce self-check FAILED", file=sys.stderr)
+        out["allreduce_selfcheck"] = "exact" if ok else "FAILED"
     if reducer is not None:
         out["allreduce_bytes_per_step"] = reducer.bytes_reduced // max(1, (args.steps + max(args.warmup, 3)
                                                                          + max(3, args.steps // 2) + 2 + args.profile_steps))

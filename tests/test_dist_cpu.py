@@ -29,7 +29,7 @@ def test_shard_batch_covers_every_scene_once():
     assert [shard_batch(64, r, 8) for r in range(8)] == [(8 * r, 8 * r + 8) for r in range(8)]
 
 
-def _worker(rank: int, world: int, port: int, wire_bf16: bool, out):
+def _worker(rank: int, world: int, port: int, wire_bf16: bool, out, keep_wire: bool = False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -41,7 +41,7 @@ def _worker(rank: int, world: int, port: int, wire_bf16: bool, out):
         for n in sizes:
             ranges.append((off, off + n))
             off += n
-        red = BucketedGradAllReduce(grad_dtype=torch.bfloat16 if wire_bf16 else None)
+        red = BucketedGradAllReduce(grad_dtype=torch.bfloat16 if wire_bf16 else None, keep_wire=keep_wire)
         red.bind(flat, ranges)
         for i in range(len(sizes)):                       # buckets become ready one by one during backward
             red.bucket_ready(i)
@@ -50,7 +50,13 @@ def _worker(rank: int, world: int, port: int, wire_bf16: bool, out):
         dist.all_gather(gathered, mine)
         expect = torch.stack(gathered).mean(0)
         tol = 2e-2 if wire_bf16 else 1e-6
-        ok = torch.allclose(flat, expect, atol=tol, rtol=tol)
+        if keep_wire:
+            # the SUM stays in the wire-dtype chunks (the consumer folds 1/world into its gradient scale); the f32
+            # buffer is left untouched
+            summed = torch.cat([c.float() for c in red.wire_chunks])
+            ok = torch.allclose(summed / world, expect, atol=tol, rtol=tol) and torch.equal(flat, mine)
+        else:
+            ok = torch.allclose(flat, expect, atol=tol, rtol=tol)
         nbytes = red.bytes_reduced
         out.put((rank, bool(ok), int(nbytes)))
     finally:
@@ -74,6 +80,21 @@ def test_bucketed_allreduce_world2_gloo(wire_bf16):
     for rank, ok, nbytes in results:
         assert ok, f"rank {rank}: averaged gradient mismatch"
         assert nbytes == total * (2 if wire_bf16 else 4)
+
+
+def test_bucketed_allreduce_keep_wire_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, True, out, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in results)
 
 
 def test_single_process_is_a_no_op():
