@@ -203,6 +203,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
   const int n_streams = 2 * n_qtiles;
   const int n_kv = g.n_kv_tiles;
 
+  pdl_launch_dependents();
   if (warp == kAttnTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_qfull, 1);
@@ -226,6 +227,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // qkv comes from the previous kernel
 
   if (warp >= kAttnTmaWarp) {
     setmaxnreg_dec<Cfg::kRegsLow>();
@@ -593,6 +595,7 @@ attention_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   const int n_qtiles = (QT == 2 && q_row0 + kTileQ < L) ? 2 : 1;
   const int n_kv = g.n_kv_tiles;
 
+  pdl_launch_dependents();
   if (warp == Cfg::kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_qfull, 1);
@@ -617,6 +620,7 @@ attention_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // qkv comes from the previous kernel
 
   if (warp >= Cfg::kTmaWarp) {
     setmaxnreg_dec<Cfg::kRegsLow>();
@@ -932,7 +936,7 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
     const double flops = 4.0 * n_seq * heads * (double)seq_len * seq_len * kHeadDim;
     const double bytes = 2.0 * (double)rows * HD * 4.0;  // q, k, v read once + out written (bf16)
     LaunchScope scope(kKindAttention, "attention_fwd", n_seq, seq_len, heads, flops, bytes, stream);
-    kern<<<grid, threads, smem_bytes, stream>>>(*tm, g);
+    VQ_CHECK_CUDA(launch_pdl(kern, grid, dim3(threads), (size_t)smem_bytes, stream, *tm, g));
   }
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;

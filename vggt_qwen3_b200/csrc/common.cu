@@ -1,3 +1,5 @@
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #include <cstring>
@@ -86,6 +88,14 @@ const CUtensorMap* get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t o
   const CUtensorMap* out = tm.get();
   cache.emplace(key, std::move(tm));
   return out;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VQ_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 int num_sms() {

@@ -38,6 +38,28 @@ const CUtensorMap* get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t o
 
 int num_sms();
 
+// Programmatic dependent launch (VQ_PDL=0 disables it): kernels of the hot chain (GEMM, attention, LayerNorm) are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization so that their prologue (barrier init, TMEM
+// allocation, descriptor prefetch) overlaps the tail of the previous kernel; see pdl_wait() in ptx.cuh.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg = cudaLaunchConfig_t();
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Launch accounting + optional CUDA-event profiling of every kernel the library launches.
 // Always counts launches; when profiling is enabled (vq_profile_enable) it brackets the launch with
 // two events on the launch stream and records (kind, tag, shape, algorithmic flops / bytes).

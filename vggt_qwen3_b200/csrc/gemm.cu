@@ -199,6 +199,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this grid's tail
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -240,6 +241,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (CG == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // everything above touched only smem, TMEM and weights; A (and the residual / C) come from the previous kernels
+  pdl_wait();
 
   const int num_kb = (g.K + kBlockK - 1) / kBlockK;
   const int tiles_per_z = g.m_tiles * g.n_tiles;
@@ -668,13 +671,15 @@ static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmAr
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   VQ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *tmA, *tmB, g));
   return VQ_OK;
 }

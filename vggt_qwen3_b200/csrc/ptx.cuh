@@ -357,6 +357,12 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// Programmatic dependent launch: `pdl_launch_dependents` lets the next kernel of the stream (when it was launched
+// with the programmatic-serialization attribute) start its prologue while this grid is still running;
+// `pdl_wait` blocks until every prerequisite grid has completed and its memory operations are visible.  Every kernel
+// that is launched with the attribute executes pdl_wait before it touches global memory written by a predecessor.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

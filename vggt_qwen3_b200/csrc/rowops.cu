@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ in, void* __restrict__ out, const float* __restrict__ gamma,
                  const float* __restrict__ beta, long long rows, int D, float eps,
                  float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_launch_dependents();
+  pdl_wait();   // `in` is the previous kernel's output
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -268,8 +270,8 @@ static int launch_ln(const void* in, void* out, const float* gamma, const float*
   LaunchScope scope(kKindRow, "layernorm", (int)rows, D, 0, 0, (double)rows * D * ((IN_F32 ? 4 : 2) + (OUT_F32 ? 4 : 2)), stream);
 #define VQ_LN_CASE(V)                                                                                      \
   case V:                                                                                                  \
-    layernorm_kernel<V, IN_F32, OUT_F32><<<grid, warps * 32, 0, stream>>>(in, out, gamma, beta, rows, D, eps, \
-                                                                          mean_out, rstd_out);             \
+    VQ_CHECK_CUDA(launch_pdl(layernorm_kernel<V, IN_F32, OUT_F32>, dim3(grid), dim3(warps * 32), 0, stream, in, out, \
+                             gamma, beta, rows, D, eps, mean_out, rstd_out));                                    \
     break;
   switch (D / 128) {
     VQ_LN_CASE(1) VQ_LN_CASE(2) VQ_LN_CASE(3) VQ_LN_CASE(4) VQ_LN_CASE(6) VQ_LN_CASE(8) VQ_LN_CASE(16)
