@@ -107,7 +107,27 @@ def report(src: str, dst: str) -> None:
                 out.write(f"  {n:30s} {v:8.3f}\n")
 
 
+def traffic(src: str, dst: str, key: str) -> None:
+    """Append {key: {"bytes": dram read + write per launch, "source": ...}} to the JSON table bench.py reads for
+    `roofline.traffic` (key = "<tag>[<m>x<n>x<k>]" as bench.py names the kernel)."""
+    import json
+    import os
+
+    txt = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d, u = dict(zip(hdr, vals)), dict(zip(hdr, units))
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tr = sum(float(d[k]) * scale.get(u[k], 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    table = json.load(open(dst)) if os.path.exists(dst) else {}
+    table[key] = {"bytes": int(tr), "source": f"profiles/{os.path.basename(src).replace('.ncu-rep', '.txt')} (ncu --set full, one launch)"}
+    json.dump(table, open(dst, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
-    {"launches": launches, "report": report}[mode](src, dst)
+    if mode == "traffic":
+        traffic(src, dst, sys.argv[4])
+    else:
+        {"launches": launches, "report": report}[mode](src, dst)
     print(open(dst).read())
