@@ -74,3 +74,35 @@ def test_product_code_never_imports_the_oracle():
     for path in (ROOT / "vggt_qwen3_b200").rglob("*.py"):
         text = path.read_text()
         assert "import oracle" not in text and "from oracle" not in text, path
+
+
+def test_new_entry_points_validate_arguments_without_gpu():
+    """f1 / f3 entry points and the attention variant switch: bad arguments come back as status codes + message."""
+    from vggt_qwen3_b200 import _lib
+
+    h = _lib.lib()
+    assert h.vq_attention_tune(-1, -1) == 0
+    assert h.vq_adamw_step(None, None, None, None, 0, None, 8, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
+    assert b"null pointer" in h.vq_last_error()
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert h.vq_adamw_step(p, p, p, p, 0, None, 6, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
+    assert b"multiple of 4" in h.vq_last_error()
+    assert h.vq_adamw_step(p, p, p, p, 0, None, 8, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
+    assert b"step counts from 1" in h.vq_last_error()
+    assert h.vq_splice_insert(None, 0, None, 8, None, None, None, None, 1, 8, 64, 4, None) == -1
+    assert h.vq_find_first_token(None, 0, 0, None, None) == -1
+
+
+def test_host_wrappers_refuse_cpu_tensors():
+    """There is no CPU fallback: the Python layer raises instead of computing on the host."""
+    from vggt_qwen3_b200 import ops
+    from vggt_qwen3_b200.optim import FusedAdamW
+
+    emb, mask = torch.zeros(1, 4, 8), torch.ones(1, 4, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.splice_insert(emb, mask, torch.zeros(1, 4, dtype=torch.int64), torch.zeros(1, 2, 8), 7)
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.ones(8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedAdamW([p], lr=1e-3).step()
