@@ -219,8 +219,29 @@ def run_b200(args) -> dict:
                 out = proj(tokens)
         return out
 
+    # e2e input pipeline: two device buffers; the images of step i+1 are copied from pinned host memory on a copy
+    # stream (DMA engine) while step i computes.  Every step still performs one full H2D copy inside the timed region,
+    # and every step ends with a stream synchronise + host read of its result, so buffer i+1 is never in use when it
+    # is overwritten.
+    copy_stream = torch.cuda.Stream(device=dev)
+    e2e_bufs = [images_dev, torch.empty_like(images_dev)]
+    e2e_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0, "primed": False}
+
+    def h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            e2e_bufs[slot].copy_(images_host, non_blocking=True)
+            e2e_ready[slot].record(copy_stream)
+
     def step_e2e():
-        images_dev.copy_(images_host, non_blocking=True)                 # H2D of this step's inputs
+        slot = e2e_state["i"] & 1
+        e2e_state["i"] += 1
+        if not e2e_state["primed"]:
+            h2d(slot)                                                    # first call only (inside the warm-up)
+            e2e_state["primed"] = True
+        torch.cuda.current_stream().wait_event(e2e_ready[slot])          # this step's inputs have landed
+        h2d(slot ^ 1)                                                    # H2D of the next step's inputs
+        images_dev = e2e_bufs[slot]
         if bwd:
             tokens = model.encode_image_tokens(images_dev)
             drain()
@@ -341,8 +362,8 @@ def run_b200(args) -> dict:
         "clocks": clocks,
         "e2e": {"value": round(frames / (ms_e2e / 1e3), 2), "unit": "frames/s", "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": images_host.numel() * 4, "d2h_bytes_per_step": 4,
-                "api": "VGGTQwen3VLM.encode_image_tokens + project_tokens (= encode_images_trainable) + backward" if bwd
-                       else "VGGTQwen3VLM.encode_images"},
+                "api": ("VGGTQwen3VLM.encode_image_tokens + project_tokens (= encode_images_trainable) + backward" if bwd
+                        else "VGGTQwen3VLM.encode_images") + "; H2D double-buffered on a copy stream, result read every step"},
         "gpu_launches": int(launches) * args.steps,
         "gpu_launches_per_step": int(launches),
         "roofline": roof,
