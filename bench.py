@@ -13,9 +13,14 @@ Workloads (BASELINE.json `configs`, synthetic 518x518 inputs, random-init weight
   c3           4 scenes x 8 frames, encode (forward) only.      c4   1 scene x 32 frames, encode only.
 
 One JSON line is printed by rank 0.  `value` = frames/s with inputs resident in HBM; `e2e` = the same step through
-the public module API (VGGTQwen3VLM.encode_images_trainable / encode_images) starting from pinned HOST images,
-including the H2D copy and a D2H read of the result.  `--impl reference` times the CPU oracle port of the
-reference path (oracle/, fp32 PyTorch on all host cores) on a bounded sample of the same workload.
+the public module API (VGGTQwen3VLM.encode_image_tokens + project_tokens / encode_images) starting from pinned HOST
+images: one H2D copy per step (double-buffered on a copy stream) and a D2H read of the result every step.
+`roofline` = the dominant kernel's algorithmic FLOPs / its CUDA-event launch time against MEASURED_PEAKS.json, with the
+DRAM traffic of the committed ncu capture (profiles/ncu_traffic.json); `cpu_baseline` = the fp32 oracle port on the
+host cores (N = 1 only).  N > 1 (torchrun): scenes sharded, the Perceiver gradient all-reduced once per step on the
+copy engines over NVLink peer memory (VQ_ALLREDUCE=nccl selects the NCCL fallback), checked bit-exactly after the
+timed region.  `--impl reference` times the CPU oracle port of the reference path (oracle/, fp32 PyTorch on all host
+cores) on a bounded sample of the same workload; under torchrun only rank 0 runs it.
 """
 from __future__ import annotations
 
