@@ -129,9 +129,11 @@ int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream);
 int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32_t seq_len, int32_t heads,
                      vq_stream_t stream);
 /* Kernel-variant overrides for tests and tuning (process-wide; negative = keep).
- *   q_tiles_per_cta : 0 = choose by sequence length (default), 1 = 128-row CTAs, two per SM (short sequences),
- *                     2 = 256-row CTAs, one per SM (long sequences)
- *   emu_pairs       : 0..4 of every 8 exponential pairs evaluated on the FMA pipe instead of the MUFU (default 2) */
+ *   q_tiles_per_cta : 0 = choose by sequence length (default: variant 4 up to 16384 keys, variant 3 beyond);
+ *                     1 / 2 = split-KV kernel with 128- / 256-row CTAs (four 64-key streams, in-place P);
+ *                     3 = wide kernel, 256-row CTAs, one per SM;  4 = wide kernel, 128-row CTAs, two per SM
+ *   emu_pairs       : 0..6 of every 8 exponential pairs evaluated on the FMA pipe instead of the MUFU (default 4;
+ *                     the split-KV kernels are instantiated for 0..4) */
 int vq_attention_tune(int32_t q_tiles_per_cta, int32_t emu_pairs);
 
 /* ------------------------------------------------------------------------------------------------

@@ -32,7 +32,7 @@ def _restore_variant():
     from vggt_qwen3_b200 import ops
 
     yield
-    ops.attention_tune(0, 3)
+    ops.attention_tune(0, 4)
 
 
 @pytest.mark.parametrize("qt", [1, 2, 3, 4])
