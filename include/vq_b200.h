@@ -188,6 +188,21 @@ int vq_splice_insert(const void* inputs_embeds, int32_t dtype, const void* atten
                      const void* vis_tokens, const int64_t* first_pos, void* out_embeds, void* out_mask, int32_t B,
                      int32_t L, int32_t hidden, int32_t n_vis, vq_stream_t stream);
 
+/* f2: image preprocessing from uint8 pixels (src/dataio/collate_multiview.py:12-19: Resize(image_size, BICUBIC) on a
+ * PIL image + CenterCrop(image_size) + ToTensor), bit-exact with Pillow's antialiased bicubic (Resample.c: 22-bit
+ * fixed-point taps, uint8 rounding after each pass) and torchvision's integer geometry; csrc/preprocess.cu.
+ *   views_hwc : uint8 [frames, H, W, 3] (device), equally sized RGB views
+ *   out_chw   : f32   [frames, 3, image_size, image_size] in [0, 1] (device) — the layout vq_aggregator_forward takes
+ *   workspace : vq_preprocess_workspace_bytes(...) bytes (device, 16-byte aligned): taps + the horizontal-pass image */
+size_t vq_preprocess_workspace_bytes(int32_t frames, int32_t H, int32_t W, int32_t image_size);
+/* Host-only (no GPU): out6 = {resized H, resized W, crop top, crop left, horizontal taps, vertical taps}; and the
+ * {first input index, tap count, taps[ksize]} rows of output indices [first, first + count) — returns ksize (> 0). */
+int vq_preprocess_geometry(int32_t H, int32_t W, int32_t image_size, int32_t* out6);
+int vq_preprocess_taps(int32_t in_size, int32_t out_size, int32_t first, int32_t count, int32_t* table,
+                       int64_t capacity);
+int vq_preprocess_views(const uint8_t* views_hwc, float* out_chw, int32_t frames, int32_t H, int32_t W,
+                        int32_t image_size, void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
 /* f3: fused AdamW step for the projector parameter group (src/train/train_sft.py:138-163: torch.optim.AdamW, defaults
  * betas (0.9, 0.999), eps 1e-8, decoupled weight decay).  One pass over HBM: reads p, m, v (f32) and the gradient
  * (f32 or bf16, multiplied by grad_scale), writes p, m, v and, when param_bf16 is non-null, the bf16 compute copy of

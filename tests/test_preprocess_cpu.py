@@ -44,3 +44,32 @@ def test_preprocess_oracle_matches_live_torchvision():
         t = transforms.Compose([transforms.Resize(size, interpolation=transforms.InterpolationMode.BICUBIC),
                                 transforms.CenterCrop(size), transforms.ToTensor()])
         assert np.array_equal(R.preprocess_view(img, size), t(Image.fromarray(img)).numpy()), (h, w, size, tv.__version__)
+
+
+def test_library_taps_and_geometry_match_the_oracle_bit_exactly():
+    """The C++ side of the GPU preprocessing (csrc/preprocess.cu) computes its geometry and fixed-point taps on the
+    host: both are checked here, without a GPU, against the oracle (which is pinned on the reference's transform)."""
+    import ctypes
+
+    from vggt_qwen3_b200 import _lib
+
+    h = _lib.lib()
+    for H, W, size in [(600, 800, 518), (480, 640, 448), (518, 518, 518), (1080, 1920, 518), (300, 200, 448),
+                       (37, 53, 28), (700, 519, 518), (40, 60, 64), (519, 518, 518), (521, 518, 518)]:
+        out6 = (ctypes.c_int32 * 6)()
+        assert h.vq_preprocess_geometry(H, W, size, out6) == 0
+        nh, nw = R.resized_output_size(H, W, size)
+        top, left = R.center_crop_box(nh, nw, size)
+        assert list(out6)[:4] == [nh, nw, top, left], (H, W, size, list(out6))
+        for in_size, out_size, first, k_lib in ((W, nw, left, out6[4]), (H, nh, top, out6[5])):
+            bounds, kk = R.precompute_coeffs(in_size, out_size)
+            ksize = kk.shape[1]
+            assert k_lib == ksize
+            table = (ctypes.c_int32 * (size * (2 + ksize)))()
+            assert h.vq_preprocess_taps(in_size, out_size, first, size, table, len(table)) == ksize
+            t = np.frombuffer(table, dtype=np.int32).reshape(size, 2 + ksize)
+            assert np.array_equal(t[:, 0], bounds[first:first + size, 0])
+            assert np.array_equal(t[:, 1], bounds[first:first + size, 1])
+            assert np.array_equal(t[:, 2:], kk[first:first + size])
+    assert h.vq_preprocess_workspace_bytes(0, 10, 10, 4) == 0 and b"geometry" in h.vq_last_error()
+    assert h.vq_preprocess_workspace_bytes(8, 600, 800, 518) >= 8 * 600 * 518 * 3

@@ -147,6 +147,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vq_attention_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.vq_attention_tune.restype = C.c_int
     lib.vq_attention_tune.argtypes = [C.c_int32, C.c_int32]
+    lib.vq_preprocess_workspace_bytes.restype = C.c_size_t
+    lib.vq_preprocess_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.vq_aggregator_workspace_bytes.restype = C.c_size_t
     lib.vq_aggregator_workspace_bytes.argtypes = [C.POINTER(AggregatorCfg)]
     lib.vq_launch_count.restype = C.c_longlong
@@ -173,6 +175,9 @@ _EXTRA_DECLS: dict[str, list] = {
     "vq_stem_finalize": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
     "vq_gather_tokens": [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp],
     "vq_splice_overwrite": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp],
+    "vq_preprocess_geometry": [_i32, _i32, _i32, _vp],
+    "vq_preprocess_taps": [_i32, _i32, _i32, _i32, _vp, _i64],
+    "vq_preprocess_views": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, C.c_size_t, _vp],
     "vq_find_first_token": [_vp, _i64, _i64, _vp, _vp],
     "vq_splice_insert": [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "vq_adamw_step": [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp],

@@ -221,3 +221,25 @@ def adamw_step(param: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Ten
                                  _dtype_code(grad.dtype), param_bf16.data_ptr() if param_bf16 is not None else None, n,
                                  step, lr, betas[0], betas[1], eps, weight_decay, grad_scale, _stream()),
         "vq_adamw_step")
+
+
+def preprocess_views(views_u8: torch.Tensor, image_size: int) -> torch.Tensor:
+    """`build_default_transform(image_size)` (src/dataio/collate_multiview.py:12-19) on a batch of equally sized RGB
+    views: uint8 [..., H, W, 3] on the GPU -> float32 [..., 3, image_size, image_size] in [0, 1], bit-exact with
+    torchvision-on-PIL (antialiased bicubic resize of the shorter edge, centre crop, ToTensor)."""
+    if not views_u8.is_cuda or views_u8.dtype != torch.uint8:
+        raise RuntimeError("preprocess_views: CUDA uint8 tensors only")
+    if views_u8.dim() < 3 or views_u8.shape[-1] != 3:
+        raise RuntimeError("preprocess_views: expected [..., H, W, 3]")
+    lead = tuple(views_u8.shape[:-3])
+    H, W = int(views_u8.shape[-3]), int(views_u8.shape[-2])
+    x = views_u8.reshape(-1, H, W, 3).contiguous()
+    frames = x.shape[0]
+    nbytes = _lib.lib().vq_preprocess_workspace_bytes(frames, H, W, image_size)
+    if nbytes == 0:
+        raise RuntimeError(_lib.lib().vq_last_error().decode())
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty((frames, 3, image_size, image_size), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().vq_preprocess_views(x.data_ptr(), out.data_ptr(), frames, H, W, image_size, ws.data_ptr(),
+                                              nbytes, _stream()), "vq_preprocess_views")
+    return out.reshape(lead + (3, image_size, image_size))
