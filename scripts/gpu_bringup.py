@@ -102,8 +102,23 @@ def case_qkv_rope(frames, grid, heads, timing=False):
     """QKV GEMM with the fused per-head QK LayerNorm + 2-D RoPE + q pre-scale epilogue against torch fp32."""
     import torch
 
-    from oracle import aggregator_ref as A
     from vggt_qwen3_b200 import ops
+
+    def rope_tables(max_pos, head_dim, freq=100.0):   # [UPSTREAM] vggt/layers/rope.py: inv_freq_j = freq^(-2j/(hd/2))
+        half = head_dim // 2
+        inv = 1.0 / (freq ** (torch.arange(0, half, 2, dtype=torch.float32) / half))
+        ang = torch.arange(max_pos + 1, dtype=torch.float32)[:, None] * inv[None, :]
+        return ang.cos(), ang.sin()
+
+    def rope_1d(t, pos, cos, sin):                    # out = t * cos + rotate_half(t) * sin, cos = cat(theta, theta)
+        c, s_ = torch.cat([cos[pos], cos[pos]], -1), torch.cat([sin[pos], sin[pos]], -1)
+        h = t.shape[-1] // 2
+        return t * c + torch.cat([-t[..., h:], t[..., :h]], -1) * s_
+
+    def rope_2d(t, pos, cos, sin):                    # first half of the head rotates with y, second half with x
+        half = t.shape[-1] // 2
+        py, px = pos[..., 0][:, None, :], pos[..., 1][:, None, :]
+        return torch.cat([rope_1d(t[..., :half], py, cos, sin), rope_1d(t[..., half:], px, cos, sin)], -1)
 
     g = torch.Generator(device="cuda").manual_seed(5)
     D, P = heads * 64, 5 + grid * grid
@@ -113,7 +128,7 @@ def case_qkv_rope(frames, grid, heads, timing=False):
     bias = torch.randn(3 * D, device="cuda", generator=g) * 0.1
     qn_w, kn_w = (torch.rand(64, device="cuda", generator=g) + 0.5 for _ in range(2))
     qn_b, kn_b = (torch.randn(64, device="cuda", generator=g) * 0.1 for _ in range(2))
-    cos, sin = (t.cuda().contiguous() for t in A.rope_tables(grid, 64))
+    cos, sin = (t.cuda().contiguous() for t in rope_tables(grid, 64))
     q_scale = 1.4426950408889634 / 8.0
     extra = dict(tokens_per_frame=P, patch_start=5, grid_w=grid, apply_qknorm_rope=1, qn_w=qn_w, qn_b=qn_b, kn_w=kn_w,
                  kn_b=kn_b, qk_eps=1e-5, q_scale=q_scale, rope_cos=cos, rope_sin=sin, rope_positions=grid + 1)
@@ -126,8 +141,8 @@ def case_qkv_rope(frames, grid, heads, timing=False):
     yy, xx = torch.meshgrid(torch.arange(grid, device="cuda"), torch.arange(grid, device="cuda"), indexing="ij")
     pos[5:, 0], pos[5:, 1] = yy.flatten() + 1, xx.flatten() + 1
     pos = pos[None].expand(frames, P, 2)
-    q = A.rope_2d(q, pos, cos, sin) * q_scale
-    k = A.rope_2d(k, pos, cos, sin)
+    q = rope_2d(q, pos, cos, sin) * q_scale
+    k = rope_2d(k, pos, cos, sin)
     ref = torch.stack([q, k, qkv[2]], 0).permute(1, 3, 0, 2, 4).reshape(M, 3 * D)
     rel = _rel(out, ref)
     msg = f"rel={rel:.3e} cos={_cos(out, ref):.6f}"
