@@ -38,6 +38,18 @@ enum {
 
 enum { VQ_BF16 = 0, VQ_F32 = 1 };
 
+/* Train-mode dropout (nn.Dropout / nn.MultiheadAttention(dropout=p) of src/models/projector_perceiver.py:33,37,42,46,49).
+ * Masks are counter-based (Philox4x32-10, csrc/philox.cuh): element (row, col) of a site's [rows, ld] tensor is dropped
+ * when its 16-bit lane of philox(seed, offset, site, row * ld/8 + col/8) is below round(p * 65536); kept elements are
+ * scaled by 1/(1-p).  Forward and backward kernels regenerate the same mask from this descriptor; nothing is stored.
+ * NULL or p == 0 means no dropout. */
+typedef struct vq_dropout_desc {
+  float p;
+  uint32_t site;    /* distinguishes the dropout sites of one forward (layer * 4 + {0 attn-prob, 1 post-attn, 2 mlp, 3 post-mlp}) */
+  uint64_t seed;    /* generator seed */
+  uint64_t offset;  /* generator offset of this forward call */
+} vq_dropout_desc;
+
 /* GEMM epilogues */
 enum {
   VQ_EPI_LINEAR = 0,   /* C = [add +] [gamma *] (alpha*acc [+ bias])                                  */
@@ -112,6 +124,10 @@ typedef struct vq_gemm_desc {
   int32_t rope_positions;            /* rows of the rope tables (max_pos + 1); 0 = unknown (tables read from global) */
   int32_t n_patches;                 /* VQ_EPI_PATCH: gh*gw */
   const float* pos_embed;            /* VQ_EPI_PATCH: [(1+n_patches), N] f32 */
+
+  /* Dropout on the epilogue value BEFORE gamma / add (unbatched LINEAR, GELU: after the activation; GELU_BWD: the
+   * incoming gradient is masked with the forward's mask); element index = (row m, column n) with ld = N. */
+  vq_dropout_desc dropout;
 } vq_gemm_desc;
 
 int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream);
@@ -276,17 +292,24 @@ int vq_aggregator_forward(const vq_aggregator_cfg* cfg, const vq_aggregator_weig
  * ---------------------------------------------------------------------------------------------- */
 
 /* softmax over the first T columns of each f32 score row -> bf16 probabilities [rows, Tp] (columns T..Tp-1 = 0).
- * The attention core of nn.MultiheadAttention (src/models/projector_perceiver.py:33,45). T, Tp <= 1024. */
+ * The attention core of nn.MultiheadAttention (src/models/projector_perceiver.py:33,45). T, Tp <= 1024.
+ * With dropout (attention-probability dropout of nn.MultiheadAttention in train mode) probs_dropped_bf16 receives
+ * mask * P / (1-p) (mask index: row, col with ld = Tp) and probs_bf16 the undropped P the backward needs. */
 int vq_softmax_fwd(const float* scores, void* probs_bf16, int64_t rows, int32_t T, int32_t ld_scores, int32_t Tp,
-                   vq_stream_t stream);
-/* dS = scale * P .* (dP - rowsum(dP .* P)) -> bf16 [rows, Tp] */
+                   const vq_dropout_desc* dropout, void* probs_dropped_bf16, vq_stream_t stream);
+/* dS = scale * P .* (dP - rowsum(dP .* P)) -> bf16 [rows, Tp]; with dropout, dP = mask * dprobs / (1-p) first. */
 int vq_softmax_bwd(const void* probs_bf16, const float* dprobs, void* dscores_bf16, int64_t rows, int32_t T,
-                   int32_t ld_dprobs, int32_t Tp, float scale, vq_stream_t stream);
+                   int32_t ld_dprobs, int32_t Tp, float scale, const vq_dropout_desc* dropout, vq_stream_t stream);
 /* LayerNorm backward (autograd of nn.LayerNorm at src/models/projector_perceiver.py:47,49): dz (bf16) from dy, the
- * saved LN input z and its row statistics; dgamma/dbeta (f32 [D]) are ACCUMULATED (+=). */
+ * saved LN input z and its row statistics; dgamma/dbeta (f32 [D]) are ACCUMULATED (+=).
+ * With dropout, dz_dropped_bf16 additionally receives mask * dz / (1-p): the gradient of the branch that went through
+ * `self.dropout(...)` before the residual add (mask index: row, col with ld = D). */
 int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const float* mean, const float* rstd,
                      const float* gamma, void* dz_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t D,
-                     vq_stream_t stream);
+                     const vq_dropout_desc* dropout, void* dz_dropped_bf16, vq_stream_t stream);
+/* Test hook: keep[r * cols + c] = 1 if element (r, c) of a [rows, ld] site survives the mask, else 0. */
+int vq_dropout_mask(uint8_t* keep, int64_t rows, int32_t cols, int32_t ld, const vq_dropout_desc* dropout,
+                    vq_stream_t stream);
 /* out[n] += sum_m x[m, n]  (bias gradients) */
 int vq_colsum(const void* x, int32_t dtype, float* out, int64_t rows, int32_t N, int64_t ld, vq_stream_t stream);
 /* f32 master -> bf16 compute copy */
@@ -301,7 +324,8 @@ int vq_reduce_batch(const void* in_bf16, float* out, int64_t n, int32_t B, int32
  * (src/models/projector_perceiver.py:70-82, layer :44-50) and its autograd backward.
  * bf16 compute copies of the f32 master weights are passed in (DeepSpeed-bf16 policy of the reference,
  * configs/deepspeed_zero3.json:4-6); gradients are produced in f32 directly from the TMEM accumulators.
- * Dropout sites (:33,37,42,46,49) are identity here (eval / p = 0).
+ * Train mode (cfg.dropout_p > 0): attention-probability dropout (:33), dropout after the attention output projection
+ * (:46), inside the MLP after GELU (:37) and after the MLP (:49), with counter-based masks (vq_dropout_desc).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct vq_perceiver_cfg {
   int32_t B, T;       /* samples, context tokens per sample (T % 8 == 0, T <= 1024) */
@@ -313,6 +337,10 @@ typedef struct vq_perceiver_cfg {
   int32_t out_dim;    /* text hidden size, 2560 */
   float ln_eps;       /* 1e-5 */
   int32_t out_dtype;  /* VQ_BF16 or VQ_F32 */
+  /* train mode: dropout probability of the four sites of every layer (0 = eval), generator seed / offset of this
+   * forward call; the backward must be given the same three values */
+  float dropout_p;
+  uint64_t dropout_seed, dropout_offset;
 } vq_perceiver_cfg;
 
 typedef struct vq_perceiver_layer_weights {

@@ -9,7 +9,9 @@ Restates, in plain matmuls on a state dict that uses the reference's own key nam
       attn_out,_ = MHA(latents, context, context)   (nn.MultiheadAttention, batch_first, packed in_proj [3E,E]:
       q/k/v = rows [0:E],[E:2E],[2E:3E]; heads = contiguous E/heads chunks; scale 1/sqrt(E/heads))
       latents = LN1(latents + attn_out); latents = LN2(latents + W2 gelu_erf(W1 latents))      (LN eps 1e-5)
-    dropout is identity here (eval mode / p = 0): parity for the dropout path is statistical, see tests.
+    train mode: the four dropout sites (:33 attention probabilities, :46, :37, :49) are applied with the SAME
+    counter-based masks the CUDA kernels regenerate (`dropout_keep_mask`, a numpy restatement of Philox4x32-10 as
+    laid out in csrc/philox.cuh), so train-mode forward and backward are compared value for value, not statistically.
   * _init_weights / parameter shapes src/models/projector_perceiver.py:13-17,56-68
   * VGGTQwen3VLM.encode_images      src/models/vggt_qwen3_vlm.py:128-162  (slice of the last aggregator output)
   * VGGTQwen3VLM.forward splice     src/models/vggt_qwen3_vlm.py:187-195  (overwrite)
@@ -80,12 +82,63 @@ def init_perceiver_state(shape: PerceiverShape, seed: int = 0, nonzero_bias: boo
     return s
 
 
+# --------------------------------------------------------------------------------------------------
+# dropout masks: Philox4x32-10, 8 elements per call (16-bit lanes), as in vggt_qwen3_b200/csrc/philox.cuh
+# --------------------------------------------------------------------------------------------------
+
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    import numpy as np
+
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85, np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3))
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0 & MASK, p1 & MASK, n2 & MASK, p0 & MASK
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def dropout_threshold(p: float) -> int:
+    return max(1, min(65535, int(p * 65536.0 + 0.5)))
+
+
+def dropout_keep_mask(rows: int, cols: int, ld: int, p: float, seed: int, offset: int, site: int) -> torch.Tensor:
+    """bool [rows, cols]: element (r, c) of a [rows, ld] dropout site is kept iff the 16-bit lane (c % 8) of
+    philox(ctr = {group lo, group hi, site, offset lo}, key = {seed lo ^ offset hi, seed hi}), group = r * ld/8 + c/8,
+    is >= round(p * 65536)."""
+    import numpy as np
+
+    if p <= 0.0:
+        return torch.ones(rows, cols, dtype=torch.bool)
+    assert ld % 8 == 0 and cols <= ld
+    r = np.arange(rows, dtype=np.uint64)[:, None]
+    g = r * np.uint64(ld // 8) + np.arange((cols + 7) // 8, dtype=np.uint64)[None, :]
+    k0 = (seed & 0xFFFFFFFF) ^ ((offset >> 32) & 0xFFFFFFFF)
+    k1 = (seed >> 32) & 0xFFFFFFFF
+    out = _philox4x32_10(g & np.uint64(0xFFFFFFFF), g >> np.uint64(32), np.uint64(site), np.uint64(offset & 0xFFFFFFFF),
+                         k0, k1)
+    lanes = np.stack([(out[j >> 1] >> np.uint64(16 * (j & 1))) & np.uint64(0xFFFF) for j in range(8)], axis=-1)
+    keep = (lanes >= np.uint64(dropout_threshold(p))).reshape(rows, -1)[:, :cols]
+    return torch.from_numpy(np.ascontiguousarray(keep))
+
+
+def _drop(x: torch.Tensor, rows: int, cols: int, ld: int, dropout, site: int) -> torch.Tensor:
+    p, seed, offset = dropout
+    keep = dropout_keep_mask(rows, cols, ld, p, seed, offset, site).to(x.device)
+    return x * keep.reshape(x.shape).to(x.dtype) * (1.0 / (1.0 - p))
+
+
 def num_layers_of(s: State) -> int:
     return 1 + max(int(k.split(".")[1]) for k in s if k.startswith("layers."))
 
 
-def perceiver_layer(s: State, p: str, latents: torch.Tensor, context: torch.Tensor, heads: int) -> torch.Tensor:
-    """PerceiverLayer.forward (src/models/projector_perceiver.py:44-50), dropout = identity."""
+def perceiver_layer(s: State, p: str, latents: torch.Tensor, context: torch.Tensor, heads: int,
+                    dropout=None, layer: int = 0) -> torch.Tensor:
+    """PerceiverLayer.forward (src/models/projector_perceiver.py:44-50).  `dropout` = None (eval) or
+    (p, seed, offset): train mode with the mask streams 4*layer + {0 attention probabilities, 1 after the attention
+    output projection, 2 after GELU, 3 after the MLP}."""
     B, Lq, E = latents.shape
     T = context.shape[1]
     hd = E // heads
@@ -97,30 +150,41 @@ def perceiver_layer(s: State, p: str, latents: torch.Tensor, context: torch.Tens
     k = k.reshape(B, T, heads, hd).transpose(1, 2)
     v = v.reshape(B, T, heads, hd).transpose(1, 2)
     att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+    drop = dropout is not None and dropout[0] > 0.0
+    if drop:   # rows = (sample, head, latent), row length padded to a multiple of 64 keys like the kernel's buffer
+        att = _drop(att, B * heads * Lq, T, (T + 63) // 64 * 64, dropout, 4 * layer + 0)
     a = (att @ v).transpose(1, 2).reshape(B, Lq, E)
     a = a @ s[f"{p}.self_attn.out_proj.weight"].t() + s[f"{p}.self_attn.out_proj.bias"]
+    if drop:
+        a = _drop(a, B * Lq, E, E, dropout, 4 * layer + 1)
     x = F.layer_norm(latents + a, (E,), s[f"{p}.norm1.weight"], s[f"{p}.norm1.bias"], 1e-5)
     h = F.gelu(x @ s[f"{p}.mlp.0.weight"].t() + s[f"{p}.mlp.0.bias"])
+    if drop:
+        h = _drop(h, B * Lq, h.shape[-1], h.shape[-1], dropout, 4 * layer + 2)
     h = h @ s[f"{p}.mlp.3.weight"].t() + s[f"{p}.mlp.3.bias"]
+    if drop:
+        h = _drop(h, B * Lq, E, E, dropout, 4 * layer + 3)
     return F.layer_norm(x + h, (E,), s[f"{p}.norm2.weight"], s[f"{p}.norm2.bias"], 1e-5)
 
 
-def perceiver_forward(s: State, tokens: torch.Tensor, heads: int) -> torch.Tensor:
-    """PerceiverProjector.forward (src/models/projector_perceiver.py:70-82): tokens [B,T,in_dim] -> [B,num_latents,out_dim]."""
+def perceiver_forward(s: State, tokens: torch.Tensor, heads: int, dropout=None) -> torch.Tensor:
+    """PerceiverProjector.forward (src/models/projector_perceiver.py:70-82): tokens [B,T,in_dim] -> [B,num_latents,out_dim].
+    `dropout` = (p, seed, offset) selects train mode with the kernels' masks."""
     B = tokens.shape[0]
     context = tokens @ s["in_proj.weight"].t() + s["in_proj.bias"]
     latents = s["latents"].unsqueeze(0).expand(B, -1, -1)
     for l in range(num_layers_of(s)):
-        latents = perceiver_layer(s, f"layers.{l}", latents, context, heads)
+        latents = perceiver_layer(s, f"layers.{l}", latents, context, heads, dropout, l)
     return latents @ s["out_proj.weight"].t() + s["out_proj.bias"]
 
 
 def perceiver_forward_backward(s: State, tokens: torch.Tensor, grad_out: torch.Tensor, heads: int,
-                               dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, State, torch.Tensor]:
+                               dtype: torch.dtype = torch.float32, dropout=None,
+                               ) -> Tuple[torch.Tensor, State, torch.Tensor]:
     """Forward + autograd backward of the restatement. Returns (out, grads by key, grad wrt tokens)."""
     leaf = {k: v.detach().to(dtype).requires_grad_(True) for k, v in s.items()}
     tok = tokens.detach().to(dtype).requires_grad_(True)
-    out = perceiver_forward(leaf, tok, heads)
+    out = perceiver_forward(leaf, tok, heads, dropout)
     out.backward(grad_out.to(dtype))
     return out.detach(), {k: v.grad for k, v in leaf.items()}, tok.grad
 

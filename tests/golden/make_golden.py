@@ -8,6 +8,10 @@ this script; tests read only the .npz files.
   perceiver_ref_small.npz   reference `PerceiverProjector` (src/models/projector_perceiver.py:53-82), eval mode:
                             its own seed-0 init (biases / LN affine / latents perturbed so those paths are live),
                             tokens, output, grad_out, every parameter gradient and the token gradient.
+  perceiver_ref_train.npz   the same reference class in TRAIN mode (dropout 0.1, src/train/train_sft.py:196) with
+                            torch.nn.functional.dropout patched to apply the counter-based masks of csrc/philox.cuh
+                            in call order (per layer: attention probabilities, post-attention, MLP, post-MLP): pins
+                            WHERE the reference drops and the site numbering; output + all gradients.
   encode_images_ref.npz     reference `VGGTQwen3VLM.encode_images` (src/models/vggt_qwen3_vlm.py:128-162) called
                             unbound on a stub whose aggregator returns an index-tagged list: pins the slice /
                             token-order contract (first num_vis_tokens rows of the view-flattened last entry).
@@ -26,6 +30,7 @@ HERE = Path(__file__).resolve().parent
 REF = Path("/root/reference")
 sys.dont_write_bytecode = True
 sys.path.insert(0, str(REF))
+sys.path.insert(0, str(HERE.parent.parent))   # oracle/ (mask function of the train-mode golden)
 
 
 def perceiver_golden():
@@ -55,6 +60,61 @@ def perceiver_golden():
         blob["grad/" + n] = p.grad.numpy()
     np.savez_compressed(HERE / "perceiver_ref_small.npz", **blob)
     print("perceiver_ref_small.npz", out.shape, float(out.detach().abs().mean()))
+
+
+def perceiver_train_golden():
+    """Reference PerceiverProjector under .train(): every dropout the reference executes (nn.Dropout modules and the
+    attention-probability dropout inside nn.MultiheadAttention all go through torch.nn.functional.dropout) is replaced
+    by the deterministic mask of its call index, so the result can be reproduced by the oracle and by the kernels."""
+    import torch.nn.functional as F
+
+    from oracle import perceiver_ref as P
+    from src.models.projector_perceiver import PerceiverConfig, PerceiverProjector
+
+    torch.manual_seed(0)
+    cfg = PerceiverConfig(latent_dim=128, num_latents=64, num_heads=2, num_layers=2, ffn_dim=256, dropout=0.1)
+    m = PerceiverProjector(cfg, in_dim=64, out_dim=96).train()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("bias") or n.endswith("in_proj_bias"):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+            elif "norm" in n and n.endswith("weight"):
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+        m.latents.mul_(25.0)
+    B, T = 3, 72   # T not a multiple of 64: the attention-probability mask is indexed with the padded row length
+    seed, offset = 20240611, 12
+    calls = []
+    real_dropout = F.dropout
+
+    def fake_dropout(x, p=0.5, training=True, inplace=False):
+        assert training and abs(p - 0.1) < 1e-9
+        site = len(calls)
+        calls.append(tuple(x.shape))
+        rows = x.numel() // x.shape[-1]
+        cols = x.shape[-1]
+        ld = (cols + 63) // 64 * 64 if site % 4 == 0 else cols
+        keep = P.dropout_keep_mask(rows, cols, ld, p, seed, offset, site).reshape(x.shape)
+        return x * keep.to(x.dtype) * (1.0 / (1.0 - p))
+
+    F.dropout = fake_dropout
+    try:
+        tokens = torch.randn(B, T, 64, generator=g, requires_grad=True)
+        out = m(tokens)
+        grad_out = torch.randn(out.shape, generator=g)
+        out.backward(grad_out)
+    finally:
+        F.dropout = real_dropout
+    # call order per layer: attention probabilities [B*H, Lq, T], post-attention [B, Lq, E], MLP [B, Lq, F], post-MLP
+    assert calls == [(B * 2, 64, T), (B, 64, 128), (B, 64, 256), (B, 64, 128)] * 2, calls
+    blob = {"cfg": np.array([cfg.latent_dim, cfg.num_latents, cfg.num_heads, cfg.num_layers, cfg.ffn_dim, 64, 96]),
+            "dropout": np.array([0.1, seed, offset]), "tokens": tokens.detach().numpy(), "out": out.detach().numpy(),
+            "grad_out": grad_out.numpy(), "grad_tokens": tokens.grad.numpy()}
+    for n, p in m.named_parameters():
+        blob["param/" + n] = p.detach().numpy()
+        blob["grad/" + n] = p.grad.numpy()
+    np.savez_compressed(HERE / "perceiver_ref_train.npz", **blob)
+    print("perceiver_ref_train.npz", out.shape, float(out.detach().abs().mean()))
 
 
 def encode_images_golden():
@@ -148,7 +208,11 @@ def dinov2_golden():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "train":   # add the train-mode golden without regenerating the others
+        perceiver_train_golden()
+        sys.exit(0)
     perceiver_golden()
+    perceiver_train_golden()
     encode_images_golden()
     insert_splice_golden()
     dinov2_golden()

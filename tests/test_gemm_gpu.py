@@ -94,3 +94,36 @@ def test_gemm_qkv_qknorm_rope_epilogue(frames, grid, heads):
 
     ok, msg = case_qkv_rope(frames, grid, heads)
     assert ok, msg
+
+
+@pytest.mark.parametrize("M,N,K,f32", [(300, 512, 256, False), (1024, 4096, 1024, False), (260, 256, 128, True)])
+def test_gemm_dropout_epilogues(M, N, K, f32):
+    """Train-mode dropout fused into the LINEAR (+ residual), GELU and GELU_BWD epilogues: the mask is the counter-based
+    one of csrc/philox.cuh (element (m, n), ld = N), kept values scaled by 1/(1-p), applied before the residual add."""
+    from oracle.perceiver_ref import dropout_keep_mask
+    from vggt_qwen3_b200 import ops
+
+    g, A, B, ref = _operands(M, N, K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    res = res if f32 else res.bfloat16()
+    p, seed, offset, site = 0.1, 77, 16, 9
+    keep = dropout_keep_mask(M, N, N, p, seed, offset, site).cuda().float() / (1.0 - p)
+    d = ops.dropout_desc(p, seed, offset, site)
+    out = ops.gemm(A, B, bias=bias, add=res, out_dtype=res.dtype, extra={"dropout": d})
+    torch.cuda.synchronize()
+    assert _rel(out, res.float() + keep * (ref + bias)) < (2e-3 if f32 else 1e-2)
+    assert torch.equal(ops.dropout_mask(M, N, N, p, seed, offset, site).bool().cpu(),
+                       dropout_keep_mask(M, N, N, p, seed, offset, site))
+    if f32:
+        return
+    out = ops.gemm(A, B, bias=bias, epilogue=ops.EPI_GELU, extra={"dropout": d})
+    torch.cuda.synchronize()
+    assert _rel(out, keep * torch.nn.functional.gelu(ref + bias)) < 1e-2
+    assert ((out == 0).float().mean() - p).abs() < 0.01
+    pre = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    x = pre.float()
+    dgelu = 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+    out = ops.gemm(A, B, epilogue=ops.EPI_GELU_BWD, aux=pre, extra={"dropout": d})
+    torch.cuda.synchronize()
+    assert _rel(out, keep * ref * dgelu) < 1e-2

@@ -18,6 +18,12 @@ EPI_LINEAR, EPI_GELU, EPI_GELU_BWD, EPI_QKV_ROPE, EPI_PATCH = 0, 1, 2, 3, 4
 _f32p = C.c_void_p
 
 
+class DropoutDesc(C.Structure):
+    """Mirror of `vq_dropout_desc`."""
+
+    _fields_ = [("p", C.c_float), ("site", C.c_uint32), ("seed", C.c_uint64), ("offset", C.c_uint64)]
+
+
 class GemmDesc(C.Structure):
     """Mirror of `vq_gemm_desc` (include/vq_b200.h)."""
 
@@ -46,6 +52,7 @@ class GemmDesc(C.Structure):
         ("rope_positions", C.c_int32),
         ("n_patches", C.c_int32),
         ("pos_embed", _f32p),
+        ("dropout", DropoutDesc),
     ]
 
 
@@ -91,6 +98,7 @@ class PerceiverCfg(C.Structure):
         ("B", C.c_int32), ("T", C.c_int32), ("in_dim", C.c_int32), ("E", C.c_int32), ("heads", C.c_int32),
         ("Lq", C.c_int32), ("layers", C.c_int32), ("ffn", C.c_int32), ("out_dim", C.c_int32),
         ("ln_eps", C.c_float), ("out_dtype", C.c_int32),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_offset", C.c_uint64),
     ]
 
 
@@ -181,9 +189,10 @@ _EXTRA_DECLS: dict[str, list] = {
     "vq_find_first_token": [_vp, _i64, _i64, _vp, _vp],
     "vq_splice_insert": [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "vq_adamw_step": [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp],
-    "vq_softmax_fwd": [_vp, _vp, _i64, _i32, _i32, _i32, _vp],
-    "vq_softmax_bwd": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp],
-    "vq_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "vq_softmax_fwd": [_vp, _vp, _i64, _i32, _i32, _i32, C.POINTER(DropoutDesc), _vp, _vp],
+    "vq_softmax_bwd": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, C.POINTER(DropoutDesc), _vp],
+    "vq_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, C.POINTER(DropoutDesc), _vp, _vp],
+    "vq_dropout_mask": [_vp, _i64, _i32, _i32, C.POINTER(DropoutDesc), _vp],
     "vq_colsum": [_vp, _i32, _vp, _i64, _i32, _i64, _vp],
     "vq_cast_f32_bf16": [_vp, _vp, _i64, _vp],
     "vq_broadcast_rows": [_vp, _vp, _i64, _i32, _vp],

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace vq {
@@ -51,6 +52,7 @@ struct GemmArgs {
   int rope_positions;  // rows of the rope tables (max_pos + 1), 0 if unknown
   int n_patches;
   const float* pos_embed;
+  DropoutParams drop;  // thr == 0: off
 };
 
 // CG = CTAs per MMA (cta_group): 1 = one CTA owns a 128 x BLOCK_N tile; 2 = a CTA pair owns a 256 x BLOCK_N tile,
@@ -610,6 +612,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int e = 0; e < kVec; ++e) v[e] += auxv[ps][e];
             }
+            if constexpr (MODE == VQ_EPI_LINEAR || MODE == VQ_EPI_GELU || MODE == VQ_EPI_GELU_BWD) {
+              if (g.drop.thr) {   // train-mode dropout: mask regenerated from (row, column), see philox.cuh
+                const int m = m_warp0 + ps * kRowsPerPass + rsub;
+                const uint32_t keep =
+                    dropout_keep8(g.drop, (uint64_t)m * (uint64_t)(g.N >> 3) + (uint64_t)(ncol >> 3)) >> (ncol & 7);
+#pragma unroll
+                for (int e = 0; e < kVec; ++e) v[e] = ((keep >> e) & 1u) ? v[e] * g.drop.scale : 0.f;
+              }
+            }
             if (g.gamma) {
 #pragma unroll
               for (int e = 0; e < kVec; ++e) v[e] *= gv[e];
@@ -802,6 +813,11 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
   g.rope_cos = d->rope_cos; g.rope_sin = d->rope_sin;
   g.rope_positions = d->rope_positions;
   g.n_patches = d->n_patches; g.pos_embed = d->pos_embed;
+  VQ_CHECK_ARG(d->dropout.p >= 0.f && d->dropout.p < 1.f, "dropout p must be in [0, 1)");
+  VQ_CHECK_ARG(d->dropout.p == 0.f || (Z0 * Z1 == 1 && (d->epilogue == VQ_EPI_LINEAR || d->epilogue == VQ_EPI_GELU ||
+                                                       d->epilogue == VQ_EPI_GELU_BWD)),
+               "dropout: unbatched LINEAR / GELU / GELU_BWD epilogues only");
+  g.drop = make_dropout_params(d->dropout.p, d->dropout.seed, d->dropout.offset, d->dropout.site);
 
   const bool f32 = d->c_dtype == VQ_F32;
   switch (d->epilogue) {

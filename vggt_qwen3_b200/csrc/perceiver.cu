@@ -7,6 +7,9 @@
 // Saved for backward (bf16 unless noted), per layer l:
 //   lat[l] [R,E] layer input | q [R,E] | kv [C,2E] | P [A,Tp] | att [R,E] | z1 [R,E] + mean1,rstd1 f32 [R]
 //   x1 [R,E] | pre [R,F] | g [R,F] | z2 [R,E] + mean2,rstd2 f32 [R];  plus ctx [C,E] and lat[layers] [R,E].
+// Train mode (cfg.dropout_p > 0) additionally keeps Pd [A,Tp] = dropout(P); `g` then holds dropout(gelu(pre)).
+// The four dropout sites of layer l use mask streams 4l + {0: attention probabilities, 1: after the attention output
+// projection, 2: after GELU, 3: after the MLP}; the backward regenerates every mask from (seed, offset, site).
 #include <math.h>
 #include <string.h>
 
@@ -34,7 +37,7 @@ Dims dims_of(const vq_perceiver_cfg* c) {
 }
 
 struct LayerSaved {
-  char *q, *kv, *P, *att, *z1, *x1, *pre, *g, *z2;
+  char *q, *kv, *P, *Pd, *att, *z1, *x1, *pre, *g, *z2;
   float *mean1, *rstd1, *mean2, *rstd2;
 };
 struct Saved {
@@ -62,6 +65,7 @@ Saved carve_saved(const vq_perceiver_cfg* c, void* base) {
     L.q = take(RE);
     L.kv = take((size_t)d.C * 2 * d.E * 2);
     L.P = take((size_t)d.A * d.Tp * 2);
+    L.Pd = c->dropout_p > 0.f ? take((size_t)d.A * d.Tp * 2) : L.P;
     L.att = take(RE);
     L.z1 = take(RE);
     L.x1 = take(RE);
@@ -79,7 +83,7 @@ Saved carve_saved(const vq_perceiver_cfg* c, void* base) {
 
 struct Work {
   float* S;       // f32 [A, Tp]  scores / dP
-  char *dlat, *dz2, *dpre, *dx1, *dz1, *datt, *dS, *dq, *dkv, *dctx_bf16, *tmp_lat;
+  char *dlat, *dz2, *dpre, *dx1, *dz1, *datt, *dS, *dq, *dkv, *dctx_bf16, *tmp_lat, *ddrop;
   float* dctx;    // f32 [C, E]
   size_t total;
 };
@@ -108,6 +112,7 @@ Work carve_work(const vq_perceiver_cfg* c, void* base) {
   w.dctx = reinterpret_cast<float*>(take((size_t)d.C * d.E * 4));
   w.dctx_bf16 = take((size_t)d.C * d.E * 2);
   w.tmp_lat = take(RE);
+  w.ddrop = take(RE);
   w.total = off;
   return w;
 }
@@ -123,13 +128,15 @@ int check_cfg(const vq_perceiver_cfg* c) {
   VQ_CHECK_ARG(c->layers > 0 && c->layers <= 64, "1..64 layers");
   VQ_CHECK_ARG(c->ffn > 0 && c->ffn % 8 == 0 && c->out_dim > 0 && c->out_dim % 8 == 0, "ffn/out_dim % 8");
   VQ_CHECK_ARG(c->out_dtype == VQ_BF16 || c->out_dtype == VQ_F32, "out_dtype");
+  VQ_CHECK_ARG(c->dropout_p >= 0.f && c->dropout_p < 1.f, "dropout_p must be in [0, 1)");
   return VQ_OK;
 }
 
 // Plain (unbatched) GEMM helper.  a_mn / b_mn select MN-major operands.
 int gemm(vq_stream_t st, int M, int N, int K, const void* A, long long lda, int a_mn, const void* Bm, long long ldb,
          int b_mn, void* Cm, long long ldc, int c_dtype, const float* bias = nullptr, const void* add = nullptr,
-         long long ldadd = 0, int epilogue = VQ_EPI_LINEAR, void* aux = nullptr, long long ldaux = 0) {
+         long long ldadd = 0, int epilogue = VQ_EPI_LINEAR, void* aux = nullptr, long long ldaux = 0,
+         const vq_dropout_desc* dropout = nullptr) {
   vq_gemm_desc g;
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K;
@@ -140,7 +147,18 @@ int gemm(vq_stream_t st, int M, int N, int K, const void* A, long long lda, int 
   g.bias = bias;
   g.add = add; g.ldadd = ldadd;
   g.aux = aux; g.ldaux = ldaux;
+  if (dropout) g.dropout = *dropout;
   return vq_gemm(&g, st);
+}
+
+// mask stream of dropout site `site` (0..3) of layer l; nullptr-equivalent (p = 0) in eval mode
+vq_dropout_desc site_of(const vq_perceiver_cfg* c, int l, int site) {
+  vq_dropout_desc d;
+  d.p = c->dropout_p;
+  d.site = (uint32_t)(4 * l + site);
+  d.seed = c->dropout_seed;
+  d.offset = c->dropout_offset;
+  return d;
 }
 
 #define RUN(expr)        \
@@ -195,25 +213,29 @@ extern "C" int vq_perceiver_forward(const vq_perceiver_cfg* c, const vq_perceive
       g.alpha = scale;
       RUN(vq_gemm(&g, st));
     }
-    RUN(vq_softmax_fwd(k.S, L.P, d.A, d.T, d.Tp, d.Tp, st));
+    const vq_dropout_desc dr0 = site_of(c, l, 0), dr1 = site_of(c, l, 1), dr2 = site_of(c, l, 2), dr3 = site_of(c, l, 3);
+    RUN(vq_softmax_fwd(k.S, L.P, d.A, d.T, d.Tp, d.Tp, &dr0, L.Pd, st));
     // att[b,:,h] = P[b,h] v[b,:,h]   (v is MN-major: keys along rows)
     {
       vq_gemm_desc g;
       memset(&g, 0, sizeof(g));
       g.M = d.Lq; g.N = d.hd; g.K = d.Tp;
       g.Z0 = d.B; g.Z1 = d.H;
-      g.A = L.P; g.lda = d.Tp; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
+      g.A = L.Pd; g.lda = d.Tp; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
       g.B = reinterpret_cast<const __nv_bfloat16*>(L.kv) + E; g.ldb = 2 * E; g.b_major = 1;
       g.b_r0 = d.T; g.b_c1 = d.hd; g.b_rows = C; g.b_cols = E;
       g.C = L.att; g.ldc = E; g.c_dtype = VQ_BF16; g.c_r0 = d.Lq; g.c_c1 = d.hd;
       RUN(vq_gemm(&g, st));
     }
-    // z1 = lat + att Wo^T + bo ; x1 = LN1(z1)
-    RUN(gemm(st, R, E, E, L.att, E, 0, lw.out_proj_w, E, 0, L.z1, E, VQ_BF16, lw.out_proj_b, s.lat[l], E));
+    // z1 = lat + drop(att Wo^T + bo) ; x1 = LN1(z1)
+    RUN(gemm(st, R, E, E, L.att, E, 0, lw.out_proj_w, E, 0, L.z1, E, VQ_BF16, lw.out_proj_b, s.lat[l], E, VQ_EPI_LINEAR,
+             nullptr, 0, &dr1));
     RUN(vq_layernorm(L.z1, VQ_BF16, L.x1, VQ_BF16, lw.norm1_w, lw.norm1_b, R, E, c->ln_eps, L.mean1, L.rstd1, st));
-    // g = gelu(x1 W1^T + b1) (pre-activation kept) ; z2 = x1 + g W2^T + b2 ; lat' = LN2(z2)
-    RUN(gemm(st, R, F, E, L.x1, E, 0, lw.fc1_w, E, 0, L.g, F, VQ_BF16, lw.fc1_b, nullptr, 0, VQ_EPI_GELU, L.pre, F));
-    RUN(gemm(st, R, E, F, L.g, F, 0, lw.fc2_w, F, 0, L.z2, E, VQ_BF16, lw.fc2_b, L.x1, E));
+    // g = drop(gelu(x1 W1^T + b1)) (pre-activation kept) ; z2 = x1 + drop(g W2^T + b2) ; lat' = LN2(z2)
+    RUN(gemm(st, R, F, E, L.x1, E, 0, lw.fc1_w, E, 0, L.g, F, VQ_BF16, lw.fc1_b, nullptr, 0, VQ_EPI_GELU, L.pre, F,
+             &dr2));
+    RUN(gemm(st, R, E, F, L.g, F, 0, lw.fc2_w, F, 0, L.z2, E, VQ_BF16, lw.fc2_b, L.x1, E, VQ_EPI_LINEAR, nullptr, 0,
+             &dr3));
     RUN(vq_layernorm(L.z2, VQ_BF16, s.lat[l + 1], VQ_BF16, lw.norm2_w, lw.norm2_b, R, E, c->ln_eps, L.mean2, L.rstd2,
                      st));
   }
@@ -262,34 +284,41 @@ extern "C" int vq_perceiver_backward(const vq_perceiver_cfg* c, const vq_perceiv
     const vq_perceiver_layer_grads& lg = gr->layers[l];
     const LayerSaved& L = s.layer[l];
     const __nv_bfloat16* Wqkv = reinterpret_cast<const __nv_bfloat16*>(lw.in_proj_w);
-    // LN2 backward
+    const bool drop = c->dropout_p > 0.f;
+    const vq_dropout_desc dr0 = site_of(c, l, 0), dr1 = site_of(c, l, 1), dr2 = site_of(c, l, 2), dr3 = site_of(c, l, 3);
+    // LN2 backward: dz2 (residual path) and dm = mask3 * dz2 / (1-p) (the branch through the post-MLP dropout)
     RUN(clear(lg.norm2_w, E)); RUN(clear(lg.norm2_b, E));
-    RUN(vq_layernorm_bwd(k.dlat, L.z2, L.mean2, L.rstd2, lw.norm2_w, k.dz2, lg.norm2_w, lg.norm2_b, R, E, st));
+    RUN(vq_layernorm_bwd(k.dlat, L.z2, L.mean2, L.rstd2, lw.norm2_w, k.dz2, lg.norm2_w, lg.norm2_b, R, E, &dr3, k.ddrop,
+                         st));
+    const char* dm = drop ? k.ddrop : k.dz2;
     // MLP backward
-    RUN(wgrad(lg.fc2_w, E, F, k.dz2, E, L.g, F, R));
+    RUN(wgrad(lg.fc2_w, E, F, dm, E, L.g, F, R));
     RUN(clear(lg.fc2_b, E));
-    RUN(vq_colsum(k.dz2, VQ_BF16, lg.fc2_b, R, E, E, st));
-    RUN(gemm(st, R, F, E, k.dz2, E, 0, lw.fc2_w, F, 1, k.dpre, F, VQ_BF16, nullptr, nullptr, 0, VQ_EPI_GELU_BWD, L.pre, F));
+    RUN(vq_colsum(dm, VQ_BF16, lg.fc2_b, R, E, E, st));
+    RUN(gemm(st, R, F, E, dm, E, 0, lw.fc2_w, F, 1, k.dpre, F, VQ_BF16, nullptr, nullptr, 0, VQ_EPI_GELU_BWD, L.pre, F,
+             &dr2));
     RUN(wgrad(lg.fc1_w, F, E, k.dpre, F, L.x1, E, R));
     RUN(clear(lg.fc1_b, F));
     RUN(vq_colsum(k.dpre, VQ_BF16, lg.fc1_b, R, F, F, st));
     RUN(gemm(st, R, E, F, k.dpre, F, 0, lw.fc1_w, E, 1, k.dx1, E, VQ_BF16, nullptr, k.dz2, E));
-    // LN1 backward
+    // LN1 backward: dz1 (residual path) and da = mask1 * dz1 / (1-p) (the branch through the post-attention dropout)
     RUN(clear(lg.norm1_w, E)); RUN(clear(lg.norm1_b, E));
-    RUN(vq_layernorm_bwd(k.dx1, L.z1, L.mean1, L.rstd1, lw.norm1_w, k.dz1, lg.norm1_w, lg.norm1_b, R, E, st));
+    RUN(vq_layernorm_bwd(k.dx1, L.z1, L.mean1, L.rstd1, lw.norm1_w, k.dz1, lg.norm1_w, lg.norm1_b, R, E, &dr1, k.ddrop,
+                         st));
+    const char* da = drop ? k.ddrop : k.dz1;
     // attention out-projection
-    RUN(wgrad(lg.out_proj_w, E, E, k.dz1, E, L.att, E, R));
+    RUN(wgrad(lg.out_proj_w, E, E, da, E, L.att, E, R));
     RUN(clear(lg.out_proj_b, E));
-    RUN(vq_colsum(k.dz1, VQ_BF16, lg.out_proj_b, R, E, E, st));
-    RUN(gemm(st, R, E, E, k.dz1, E, 0, lw.out_proj_w, E, 1, k.datt, E, VQ_BF16));
+    RUN(vq_colsum(da, VQ_BF16, lg.out_proj_b, R, E, E, st));
+    RUN(gemm(st, R, E, E, da, E, 0, lw.out_proj_w, E, 1, k.datt, E, VQ_BF16));
     // attention core, per (sample, head)
     __nv_bfloat16* dkv = reinterpret_cast<__nv_bfloat16*>(k.dkv);
     const __nv_bfloat16* kv = reinterpret_cast<const __nv_bfloat16*>(L.kv);
-    {  // dV = P^T datt  -> dkv[:, E + h*hd]
+    {  // dV = Pd^T datt  -> dkv[:, E + h*hd]   (Pd = dropout(P), = P in eval mode)
       vq_gemm_desc g;
       memset(&g, 0, sizeof(g));
       g.M = d.T; g.N = d.hd; g.K = d.Lq; g.Z0 = d.B; g.Z1 = d.H;
-      g.A = L.P; g.lda = d.Tp; g.a_major = 1; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
+      g.A = L.Pd; g.lda = d.Tp; g.a_major = 1; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
       g.B = k.datt; g.ldb = E; g.b_major = 1; g.b_r0 = d.Lq; g.b_c1 = d.hd; g.b_rows = R; g.b_cols = E;
       g.C = dkv + E; g.ldc = 2 * E; g.c_dtype = VQ_BF16; g.c_r0 = d.T; g.c_c1 = d.hd;
       RUN(vq_gemm(&g, st));
@@ -303,7 +332,7 @@ extern "C" int vq_perceiver_backward(const vq_perceiver_cfg* c, const vq_perceiv
       g.C = k.S; g.ldc = d.Tp; g.c_dtype = VQ_F32; g.c_r0 = (long long)d.H * d.Lq; g.c_r1 = d.Lq;
       RUN(vq_gemm(&g, st));
     }
-    RUN(vq_softmax_bwd(L.P, k.S, k.dS, d.A, d.T, d.Tp, d.Tp, scale, st));
+    RUN(vq_softmax_bwd(L.P, k.S, k.dS, d.A, d.T, d.Tp, d.Tp, scale, &dr0, st));
     {  // dq = dS k -> [R, E]
       vq_gemm_desc g;
       memset(&g, 0, sizeof(g));

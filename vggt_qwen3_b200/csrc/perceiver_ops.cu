@@ -1,9 +1,16 @@
 // HBM-bound kernels of the Perceiver projector forward/backward: row softmax (fwd/bwd), LayerNorm backward,
 // column sums (bias / LayerNorm-affine gradients), dtype casts, latent broadcast and batch reduction.
 #include "common.cuh"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace vq {
+
+// keep bit of element (r, c) of a [rows, ld] dropout site
+__device__ __forceinline__ bool dropout_keep(const DropoutParams& d, long long r, int c, int ld) {
+  const uint64_t group = (uint64_t)r * (uint64_t)(ld >> 3) + (uint64_t)(c >> 3);
+  return (dropout_keep8(d, group) >> (c & 7)) & 1u;
+}
 
 __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
@@ -22,7 +29,7 @@ constexpr int kMaxPerLane = 32;  // T <= 1024
 
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, long long rows, int T, int lds,
-                   int Tp) {
+                   int Tp, const DropoutParams drop, __nv_bfloat16* __restrict__ pd) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -47,14 +54,22 @@ softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, l
 #pragma unroll
   for (int i = 0; i < kMaxPerLane; ++i) {
     const int c = i * 32 + lane;
-    if (c < Tp) dst[c] = __float2bfloat16(v[i] * inv);
+    if (c < Tp) {
+      const __nv_bfloat16 pv = __float2bfloat16(v[i] * inv);
+      dst[c] = pv;
+      // attention-probability dropout acts on the bf16 probability the P V product would otherwise read
+      if (drop.thr)
+        pd[r * Tp + c] = (c < T && dropout_keep(drop, r, c, Tp)) ? __float2bfloat16(__bfloat162float(pv) * drop.scale)
+                                                                 : __float2bfloat16(0.f);
+    }
   }
 }
 
 // dS = scale * P .* (dP - rowsum(dP .* P));  P bf16 [rows, Tp], dP f32 [rows, ld], dS bf16 [rows, Tp] (zero padded)
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ dp,
-                   __nv_bfloat16* __restrict__ ds, long long rows, int T, int lddp, int Tp, float scale) {
+                   __nv_bfloat16* __restrict__ ds, long long rows, int T, int lddp, int Tp, float scale,
+                   const DropoutParams drop) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -65,6 +80,7 @@ softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict_
     const int c = i * 32 + lane;
     pv[i] = c < T ? __bfloat162float(p[r * Tp + c]) : 0.f;
     dv[i] = c < T ? dp[r * lddp + c] : 0.f;
+    if (drop.thr && c < T) dv[i] = dropout_keep(drop, r, c, Tp) ? dv[i] * drop.scale : 0.f;
     dot += pv[i] * dv[i];
   }
   dot = wsum(dot);
@@ -81,7 +97,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                        const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dz, long long rows, int D) {
+                        const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dz, long long rows, int D,
+                        const DropoutParams drop, __nv_bfloat16* __restrict__ dzd) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -113,7 +130,25 @@ layernorm_bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
     u.x = pack_bf16x2(rs * (dyg[i][0] - s1 - xh[i][0] * s2), rs * (dyg[i][1] - s1 - xh[i][1] * s2));
     u.y = pack_bf16x2(rs * (dyg[i][2] - s1 - xh[i][2] * s2), rs * (dyg[i][3] - s1 - xh[i][3] * s2));
     *reinterpret_cast<uint2*>(dz + r * D + col) = u;
+    if (drop.thr) {
+      // gradient of the dropped branch: the mask acts on the bf16 dz the residual path sees
+      const uint32_t keep = dropout_keep8(drop, (uint64_t)r * (uint64_t)(D >> 3) + (uint64_t)(col >> 3)) >> (col & 4);
+      uint2 w;
+      w.x = pack_bf16x2((keep & 1u) ? bf16_lo(u.x) * drop.scale : 0.f, (keep & 2u) ? bf16_hi(u.x) * drop.scale : 0.f);
+      w.y = pack_bf16x2((keep & 4u) ? bf16_lo(u.y) * drop.scale : 0.f, (keep & 8u) ? bf16_hi(u.y) * drop.scale : 0.f);
+      *reinterpret_cast<uint2*>(dzd + r * D + col) = w;
+    }
   }
+}
+
+// test hook: materialise a site's mask
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(uint8_t* __restrict__ keep, long long rows, int cols, int ld, const DropoutParams drop) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = (int)(i - r * cols);
+  keep[i] = drop.thr ? (dropout_keep(drop, r, c, ld) ? 1 : 0) : 1;
 }
 
 // (2) dgamma[n] += sum_m dy*xhat, dbeta[n] += sum_m dy.  Each thread owns 8 adjacent columns (128-bit loads) and
@@ -227,37 +262,69 @@ reduce_batch_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ ou
 
 using namespace vq;
 
+static DropoutParams params_of(const vq_dropout_desc* d) {
+  if (!d) return make_dropout_params(0.f, 0, 0, 0);
+  return make_dropout_params(d->p, d->seed, d->offset, d->site);
+}
+#define VQ_CHECK_DROPOUT(d) VQ_CHECK_ARG(!(d) || ((d)->p >= 0.f && (d)->p < 1.f), "dropout p must be in [0, 1)")
+
+extern "C" int vq_dropout_mask(uint8_t* keep, int64_t rows, int32_t cols, int32_t ld, const vq_dropout_desc* dropout,
+                               vq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(keep && rows > 0 && cols > 0 && ld >= cols && ld % 8 == 0, "dropout_mask arguments (ld % 8 == 0)");
+  VQ_CHECK_DROPOUT(dropout);
+  const long long n = (long long)rows * cols;
+  LaunchScope scope(kKindRow, "dropout_mask", (int)rows, cols, 0, 0, (double)n, stream);
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keep, rows, cols, ld, params_of(dropout));
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
+}
+
 extern "C" int vq_softmax_fwd(const float* scores, void* probs_bf16, int64_t rows, int32_t T, int32_t ld_scores,
-                              int32_t Tp, vq_stream_t stream_) {
+                              int32_t Tp, const vq_dropout_desc* dropout, void* probs_dropped_bf16,
+                              vq_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(scores && probs_bf16, "null pointer");
+  VQ_CHECK_DROPOUT(dropout);
+  const DropoutParams drop = params_of(dropout);
+  VQ_CHECK_ARG(!drop.thr || (probs_dropped_bf16 && Tp % 8 == 0), "dropout needs probs_dropped and Tp % 8 == 0");
   VQ_CHECK_ARG(rows > 0 && T > 0 && T <= 32 * kMaxPerLane && Tp >= T && Tp <= 32 * kMaxPerLane && ld_scores >= T,
                "softmax geometry (T <= 1024)");
   LaunchScope scope(kKindRow, "softmax_fwd", (int)rows, T, 0, 0, (double)rows * (T * 4.0 + Tp * 2.0), stream);
   softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
-      scores, reinterpret_cast<__nv_bfloat16*>(probs_bf16), rows, T, ld_scores, Tp);
+      scores, reinterpret_cast<__nv_bfloat16*>(probs_bf16), rows, T, ld_scores, Tp, drop,
+      reinterpret_cast<__nv_bfloat16*>(probs_dropped_bf16));
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
 }
 
 extern "C" int vq_softmax_bwd(const void* probs_bf16, const float* dprobs, void* dscores_bf16, int64_t rows,
-                              int32_t T, int32_t ld_dprobs, int32_t Tp, float scale, vq_stream_t stream_) {
+                              int32_t T, int32_t ld_dprobs, int32_t Tp, float scale, const vq_dropout_desc* dropout,
+                              vq_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(probs_bf16 && dprobs && dscores_bf16, "null pointer");
+  VQ_CHECK_DROPOUT(dropout);
+  const DropoutParams drop = params_of(dropout);
+  VQ_CHECK_ARG(!drop.thr || Tp % 8 == 0, "dropout needs Tp % 8 == 0");
   VQ_CHECK_ARG(rows > 0 && T > 0 && Tp >= T && Tp <= 32 * kMaxPerLane && ld_dprobs >= T, "softmax geometry");
   LaunchScope scope(kKindRow, "softmax_bwd", (int)rows, T, 0, 0, (double)rows * (T * 6.0 + Tp * 2.0), stream);
   softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(probs_bf16), dprobs, reinterpret_cast<__nv_bfloat16*>(dscores_bf16),
-      rows, T, ld_dprobs, Tp, scale);
+      rows, T, ld_dprobs, Tp, scale, drop);
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
 }
 
 extern "C" int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const float* mean, const float* rstd,
                                 const float* gamma, void* dz_bf16, float* dgamma, float* dbeta, int64_t rows,
-                                int32_t D, vq_stream_t stream_) {
+                                int32_t D, const vq_dropout_desc* dropout, void* dz_dropped_bf16,
+                                vq_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(dy_bf16 && z_bf16 && mean && rstd && gamma && dz_bf16 && dgamma && dbeta, "null pointer");
+  VQ_CHECK_DROPOUT(dropout);
+  const DropoutParams drop = params_of(dropout);
+  VQ_CHECK_ARG(!drop.thr || dz_dropped_bf16, "dropout needs dz_dropped");
+  __nv_bfloat16* dzd = reinterpret_cast<__nv_bfloat16*>(dz_dropped_bf16);
   VQ_CHECK_ARG(rows > 0 && D % 128 == 0, "geometry");
   const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(z_bf16);
@@ -267,7 +334,7 @@ extern "C" int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const f
     LaunchScope scope(kKindRow, "layernorm_bwd_dz", (int)rows, D, 0, 0, (double)rows * D * 6.0, stream);
 #define VQ_LNB_CASE(V)                                                                                  \
   case V:                                                                                               \
-    layernorm_bwd_dz_kernel<V><<<grid, 256, 0, stream>>>(dy, z, mean, rstd, gamma, dz, rows, D);        \
+    layernorm_bwd_dz_kernel<V><<<grid, 256, 0, stream>>>(dy, z, mean, rstd, gamma, dz, rows, D, drop, dzd); \
     break;
     switch (D / 128) {
       VQ_LNB_CASE(1) VQ_LNB_CASE(2) VQ_LNB_CASE(4) VQ_LNB_CASE(8) VQ_LNB_CASE(16) VQ_LNB_CASE(32)

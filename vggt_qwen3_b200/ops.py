@@ -141,19 +141,38 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return (out, mean, rstd) if return_stats else out
 
 
-def layernorm_bwd(dy: torch.Tensor, z: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor):
-    """Returns (dz bf16, dgamma f32, dbeta f32) for bf16 dy and saved LN input z."""
+def dropout_desc(p: float, seed: int, offset: int, site: int) -> "_lib.DropoutDesc":
+    d = _lib.DropoutDesc()
+    d.p, d.site, d.seed, d.offset = float(p), int(site), int(seed), int(offset)
+    return d
+
+
+def dropout_mask(rows: int, cols: int, ld: int, p: float, seed: int, offset: int, site: int,
+                 device: Optional[torch.device] = None) -> torch.Tensor:
+    """uint8 [rows, cols] keep-mask of a dropout site (test hook: the mask the kernels regenerate on the fly)."""
+    keep = torch.empty(rows, cols, dtype=torch.uint8, device=device or torch.device("cuda"))
+    d = dropout_desc(p, seed, offset, site)
+    _lib.check(_lib.lib().vq_dropout_mask(keep.data_ptr(), rows, cols, ld, C.byref(d), _stream()), "vq_dropout_mask")
+    return keep
+
+
+def layernorm_bwd(dy: torch.Tensor, z: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
+                  dropout: Optional["_lib.DropoutDesc"] = None):
+    """Returns (dz bf16, dgamma f32, dbeta f32) for bf16 dy and saved LN input z; with `dropout` additionally the
+    masked + rescaled dz of the branch that went through dropout before the residual add."""
     _req(dy, torch.bfloat16, "dy")
     _req(z, torch.bfloat16, "z")
     rows, D = z.shape
     dz = torch.empty_like(z)
     dgamma = torch.zeros(D, device=z.device, dtype=torch.float32)
     dbeta = torch.zeros(D, device=z.device, dtype=torch.float32)
+    dzd = torch.empty_like(z) if dropout is not None else None
     _lib.check(
         _lib.lib().vq_layernorm_bwd(dy.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                    dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D, _stream()),
+                                    dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D,
+                                    C.byref(dropout) if dropout is not None else None, _ptr(dzd), _stream()),
         "vq_layernorm_bwd")
-    return dz, dgamma, dbeta
+    return (dz, dgamma, dbeta) if dropout is None else (dz, dgamma, dbeta, dzd)
 
 
 def splice_overwrite(inputs_embeds: torch.Tensor, input_ids: torch.Tensor, features: torch.Tensor, image_id: int,

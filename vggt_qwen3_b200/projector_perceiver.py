@@ -10,6 +10,15 @@ The torch.nn submodules are parameter containers; `forward` runs `vq_perceiver_f
 kernels) and autograd is provided by `_PerceiverFunction`, whose backward is `vq_perceiver_backward`.
 f32 master parameters get bf16 compute copies (refreshed when a parameter's version counter changes);
 gradients come back in f32.  No CPU fallback: CPU tensors raise.
+
+Train mode (`.train()` with `config.dropout > 0`, how the reference trains: src/train/train_sft.py:196) applies the
+reference's four dropout sites per layer (:33 attention probabilities, :46 after the attention output projection, :37
+inside the MLP, :49 after the MLP) with counter-based Philox masks: (seed, offset) are taken from torch's CUDA
+generator like any ATen dropout (reproducible under `torch.manual_seed`), the backward regenerates the masks.
+
+Buffers: the activations kept for backward, the scratch workspace and ONE flat f32 gradient buffer (`grad_flat`,
+`p.grad` of every parameter is a view into it) persist across steps; gradient accumulation (`p.grad` still set when
+the next backward runs, as inside `accelerator.accumulate`) is done by the kernels directly into that buffer.
 """
 from __future__ import annotations
 
@@ -84,6 +93,8 @@ class PerceiverProjector(nn.Module):
         self.apply(_xavier_linear_init)
         self._compute: Optional[dict] = None
         self._grad_flat: Optional[torch.Tensor] = None
+        self._grad_view_list: Optional[List[torch.Tensor]] = None
+        self._buffers: dict = {}   # (kind, nbytes, device) -> persistent uint8 scratch
         # called as hook(layer_index) right after the kernels producing that bucket's gradients are enqueued
         # (layer_index = num_layers for out_proj, L-1..0 for the layers, -1 for in_proj + latents)
         self.grad_ready_hook: Optional[Callable[[int], None]] = None
@@ -148,21 +159,69 @@ class PerceiverProjector(nn.Module):
             cc["structs"] = (w, arr)
         return cc
 
-    def _grad_views(self, device: torch.device) -> List[torch.Tensor]:
-        """Views, in `_ordered_params` order, into one flat f32 gradient buffer (fresh per backward so that
-        autograd can take ownership of the views without aliasing a previous step's .grad)."""
-        params = self._ordered_params()
-        total = sum((p.numel() + 63) // 64 * 64 for p in params)
-        flat = torch.empty(total, device=device, dtype=torch.float32)
-        views, off = [], 0
-        for p in params:
-            views.append(flat[off:off + p.numel()].view(p.shape))
+    def grad_offsets(self) -> List[int]:
+        """Element offset of every parameter (in `_ordered_params` order) inside the flat gradient buffer; each
+        tensor is padded to a multiple of 64 elements so that every view is 256-byte aligned."""
+        offs, off = [], 0
+        for p in self._ordered_params():
+            offs.append(off)
             off += (p.numel() + 63) // 64 * 64
-        self._grad_flat = flat
+        return offs + [off]
+
+    def _grad_views(self, device: torch.device, fresh: bool = False) -> List[torch.Tensor]:
+        """Views, in `_ordered_params` order, into the flat f32 gradient buffer.  The buffer persists across steps
+        (`grad_flat`); `fresh=True` returns views into a new temporary buffer instead (used when some `p.grad` is
+        set but does not alias the persistent buffer, so that autograd accumulates the ordinary way)."""
+        params = self._ordered_params()
+        offs = self.grad_offsets()
+        if not fresh and self._grad_flat is not None and self._grad_flat.device == device \
+                and self._grad_flat.numel() == offs[-1]:
+            return self._grad_view_list
+        flat = torch.empty(offs[-1], device=device, dtype=torch.float32)
+        views = [flat[o:o + p.numel()].view(p.shape) for p, o in zip(params, offs)]
+        if not fresh:
+            self._grad_flat, self._grad_view_list = flat, views
         return views
 
-    def _cfg(self, B: int, T: int, out_dtype: torch.dtype) -> PerceiverCfg:
+    @property
+    def grad_flat(self) -> Optional[torch.Tensor]:
+        """The flat f32 gradient buffer of the last backward (None before the first)."""
+        return self._grad_flat
+
+    def _scratch(self, kind: str, nbytes: int, device: torch.device) -> torch.Tensor:
+        """Persistent 1024-byte-aligned scratch (`saved` activations / workspace), reused while the size matches."""
+        buf = self._buffers.get(kind)
+        if buf is None or buf.numel() < nbytes + 1024 or buf.device != device:
+            buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            self._buffers[kind] = buf
+        return buf
+
+    def _lease_saved(self, nbytes: int, device: torch.device) -> "_Lease":
+        """A `saved`-activations buffer from the module's pool (stable addresses across steps: the TMA descriptors
+        cached by the library keep hitting); it goes back to the pool when the autograd graph that holds it dies."""
+        pool = self._buffers.setdefault("saved_pool", [])
+        for i, buf in enumerate(pool):
+            if buf.numel() >= nbytes + 1024 and buf.device == device:
+                return _Lease(pool, pool.pop(i))
+        del pool[:]     # shape changed: drop stale buffers
+        return _Lease(pool, torch.empty(nbytes + 1024, dtype=torch.uint8, device=device))
+
+    def _draw_dropout(self, device: torch.device):
+        """(p, seed, offset) of this forward: eval mode or dropout 0 -> (0, 0, 0); train mode advances the CUDA
+        generator's Philox offset exactly like an ATen dropout kernel would."""
+        p = float(self.config.dropout)
+        if not self.training or p <= 0.0:
+            return 0.0, 0, 0
+        if not 0.0 <= p < 1.0:
+            raise ValueError(f"dropout probability must be in [0, 1), got {p}")
+        gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+        seed, offset = int(gen.initial_seed()), int(gen.get_offset())
+        gen.set_offset(offset + 4)
+        return p, seed & 0xFFFFFFFFFFFFFFFF, offset
+
+    def _cfg(self, B: int, T: int, out_dtype: torch.dtype, dropout=(0.0, 0, 0)) -> PerceiverCfg:
         c = PerceiverCfg()
+        c.dropout_p, c.dropout_seed, c.dropout_offset = dropout
         cfg = self.config
         c.B, c.T, c.in_dim = B, T, self.in_dim
         c.E, c.heads, c.Lq, c.layers, c.ffn = cfg.latent_dim, cfg.num_heads, cfg.num_latents, cfg.num_layers, cfg.ffn_dim
@@ -178,11 +237,18 @@ class PerceiverProjector(nn.Module):
             raise ValueError(f"expected tokens [B, T, {self.in_dim}], got {tuple(tokens.shape)}")
         if not tokens.is_cuda:
             raise RuntimeError("PerceiverProjector runs on sm_100a only: tokens must be a CUDA tensor (no CPU fallback)")
-        if self.training and self.config.dropout > 0.0:
-            raise NotImplementedError(
-                "dropout > 0 in training mode is not implemented in the sm_100a kernels yet; "
-                "call .eval() or build the projector with PerceiverConfig(dropout=0.0)")
         return _PerceiverFunction.apply(self, tokens, *self._ordered_params())
+
+
+class _Lease:
+    """Returns `buf` to `pool` when the last reference (the autograd ctx) goes away."""
+
+    def __init__(self, pool: list, buf: torch.Tensor) -> None:
+        self.pool, self.buf = pool, buf
+
+    def __del__(self) -> None:
+        if len(self.pool) < 4:
+            self.pool.append(self.buf)
 
 
 class _PerceiverFunction(torch.autograd.Function):
@@ -192,7 +258,7 @@ class _PerceiverFunction(torch.autograd.Function):
         dev = tokens.device
         B, T, _ = tokens.shape
         out_dtype = torch.float32 if module.in_proj.weight.dtype == torch.float32 else torch.bfloat16
-        cfg = module._cfg(B, T, out_dtype)
+        cfg = module._cfg(B, T, out_dtype, module._draw_dropout(dev))
         cc = module._refresh_compute_copies(dev)
         tok = tokens.detach().reshape(B * T, -1)
         tok = tok.contiguous() if tok.dtype == torch.bfloat16 else tok.to(torch.bfloat16)
@@ -200,14 +266,15 @@ class _PerceiverFunction(torch.autograd.Function):
         work_bytes = lib.vq_perceiver_workspace_bytes(C.byref(cfg))
         if saved_bytes == 0 or work_bytes == 0:
             _lib.check(-1, "vq_perceiver_saved_bytes")
-        saved = torch.empty(saved_bytes + 1024, dtype=torch.uint8, device=dev)
-        work = torch.empty(work_bytes + 1024, dtype=torch.uint8, device=dev)
+        lease = module._lease_saved(saved_bytes, dev)   # returns to the module's pool when the graph is freed
+        saved = lease.buf
+        work = module._scratch("work", work_bytes, dev)
         out = torch.empty(B, module.config.num_latents, module.out_dim, dtype=out_dtype, device=dev)
         a1024 = lambda t: (t.data_ptr() + 1023) // 1024 * 1024
         rc = lib.vq_perceiver_forward(C.byref(cfg), C.byref(cc["structs"][0]), tok.data_ptr(), out.data_ptr(),
                                       a1024(saved), a1024(work), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "vq_perceiver_forward")
-        ctx.module, ctx.cfg, ctx.saved, ctx.tok, ctx.work = module, cfg, saved, tok, work
+        ctx.module, ctx.cfg, ctx.saved, ctx.tok, ctx.work, ctx.lease = module, cfg, saved, tok, work, lease
         ctx.tokens_dtype = tokens.dtype
         ctx.tokens_shape = tokens.shape
         return out
@@ -221,7 +288,20 @@ class _PerceiverFunction(torch.autograd.Function):
         cc = module._refresh_compute_copies(dev)
         g = grad_out.detach().reshape(cfg.B * cfg.Lq, cfg.out_dim)
         g = g.contiguous() if g.dtype == torch.bfloat16 else g.to(torch.bfloat16)
+        params = module._ordered_params()
+        # Gradient hand-off.  `grad_flat` persists; three cases:
+        #  (a) every p.grad is None (zero_grad(set_to_none=True), first step): the kernels OVERWRITE the flat buffer and
+        #      the views are returned to autograd, which adopts them as p.grad without a copy;
+        #  (b) every p.grad IS the matching view (gradient accumulation, zero_grad(set_to_none=False)): the kernels
+        #      ACCUMULATE into the flat buffer in place and autograd gets no gradient tensors (nothing to add);
+        #  (c) anything else (a foreign p.grad): a temporary buffer, ordinary autograd accumulation.
         views = module._grad_views(dev)
+        has_grad = [p.grad is not None for p in params]
+        aliased = all(h and p.grad.data_ptr() == v.data_ptr() and p.grad.dtype == torch.float32
+                      for h, p, v in zip(has_grad, params, views))
+        in_place = aliased and any(has_grad)
+        if any(has_grad) and not in_place:
+            views = module._grad_views(dev, fresh=True)
         n = len(_LAYER_PARAM_ORDER)
         gr = PerceiverGrads()
         gr.latents, gr.in_proj_w, gr.in_proj_b = views[0].data_ptr(), views[1].data_ptr(), views[2].data_ptr()
@@ -231,21 +311,37 @@ class _PerceiverFunction(torch.autograd.Function):
                 setattr(arr[l], field, views[3 + l * n + j].data_ptr())
         gr.layers = arr
         gr.out_proj_w, gr.out_proj_b = views[-2].data_ptr(), views[-1].data_ptr()
-        gr.accumulate = 0
+        gr.accumulate = 1 if in_place else 0
         need_tok = ctx.needs_input_grad[1]
         grad_tok = torch.empty(cfg.B * cfg.T, cfg.in_dim, dtype=torch.float32, device=dev) if need_tok else None
         hook = module.grad_ready_hook
-        cb = LayerDoneFn((lambda layer, _user: hook(int(layer))) if hook is not None else (lambda layer, _user: None))
+        hook_error: List[BaseException] = []
+
+        def on_layer_done(layer, _user):   # a ctypes callback must not raise: stash the exception, re-raise below
+            if hook is None or hook_error:
+                return
+            try:
+                hook(int(layer))
+            except BaseException as exc:  # noqa: BLE001
+                hook_error.append(exc)
+
+        cb = LayerDoneFn(on_layer_done)
         a1024 = lambda t: (t.data_ptr() + 1023) // 1024 * 1024
         rc = lib.vq_perceiver_backward(
             C.byref(cfg), C.byref(cc["structs"][0]), ctx.tok.data_ptr(), g.data_ptr(), a1024(ctx.saved), C.byref(gr),
             grad_tok.data_ptr() if need_tok else None, a1024(ctx.work), cb, None,
             torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "vq_perceiver_backward")
-        params = module._ordered_params()
-        grads = [v if p.dtype == torch.float32 else v.to(p.dtype) for v, p in zip(views, params)]
+        if hook_error:
+            raise RuntimeError("grad_ready_hook failed during the Perceiver backward") from hook_error[0]
+        if in_place:
+            grads = [None] * len(params)
+        else:
+            # fresh tensor objects over the same storage: autograd adopts a gradient without copying only when it
+            # holds the sole reference to it (the module keeps its own view objects)
+            grads = [v.view(p.shape) if p.dtype == torch.float32 else v.to(p.dtype) for v, p in zip(views, params)]
         gt = None
         if need_tok:
             gt = grad_tok.view(ctx.tokens_shape).to(ctx.tokens_dtype)
-        ctx.saved = ctx.work = ctx.tok = None
+        ctx.saved = ctx.work = ctx.tok = ctx.lease = None
         return (None, gt, *grads)
