@@ -193,6 +193,31 @@ int vq_splice_overwrite(void* inputs_embeds, int32_t dtype, const int64_t* input
                         int32_t L, int32_t hidden, int32_t n_feat, int64_t image_id, int32_t* overflow_count,
                         vq_stream_t stream);
 
+/* a11 + f1: geometry tokens and the fused training splice (csrc/geom.cu).
+ * vq_geom_head_forward: encode_geom + geom_head (src/models/vggt_qwen3_vlm.py:51-56,164-177):
+ *   pooled[b] = mean over views of cat(parts[0..3]) (R 9 | t 3 | K 9 | depth_hist 16; parts[k] f32 [B, V, widths[k]],
+ *   NULL = zeros like the reference's `geom_token.get(key, zeros)`), pre = pooled W1^T + b1, act = silu(pre),
+ *   y = act W2^T + b2 -> f32 [B, H].  pooled / pre / act are kept for the backward.  Weights f32 [H, in], [H, H].
+ * vq_geom_head_backward: dW1, db1, dW2, db2 (overwritten, or += when accumulate) from dy [B, H]; scratch: B*H floats. */
+int vq_geom_head_forward(const float* const* parts, const int32_t* widths, const float* w1, const float* b1,
+                         const float* w2, const float* b2, float* pooled, float* pre, float* act, float* y, int32_t B,
+                         int32_t V, int32_t in_dim, int32_t H, vq_stream_t stream);
+int vq_geom_head_backward(const float* dy, const float* pooled, const float* pre, const float* act, const float* w2,
+                          float* dw1, float* db1, float* dw2, float* db2, float* scratch, int32_t B, int32_t in_dim,
+                          int32_t H, int32_t accumulate, vq_stream_t stream);
+/* vq_splice_features: vq_splice_overwrite with the span cat([geom.expand(n_geom), vis])[b] never materialised
+ * (src/models/vggt_qwen3_vlm.py:187-195): feature row t < n_geom is geom[b] (f32 [B, hidden], cast on the fly), row
+ * t >= n_geom is vis[b, t - n_geom] (embedding dtype, [B, n_vis, hidden]).
+ * vq_splice_features_backward: autograd backward of that assignment in one launch: d_embeds = grad with the written
+ * rows zeroed (NULL to skip), d_geom f32 [B, hidden] / d_vis f32 [B, n_vis, hidden] = gradient rows gathered back to
+ * the feature they were written from (either may be NULL). */
+int vq_splice_features(void* inputs_embeds, int32_t dtype, const int64_t* input_ids, const float* geom, int32_t n_geom,
+                       const void* vis, int32_t n_vis, int32_t B, int32_t L, int32_t hidden, int64_t image_id,
+                       int32_t* overflow_count, vq_stream_t stream);
+int vq_splice_features_backward(const void* grad, int32_t dtype, const int64_t* input_ids, void* d_embeds, float* d_geom,
+                                float* d_vis, int32_t n_geom, int32_t n_vis, int32_t B, int32_t L, int32_t hidden,
+                                int64_t image_id, vq_stream_t stream);
+
 /* f1: inference splice (src/inference/qa_inference.py:119-145, src/inference/arkit_inference.py:182-214).
  * vq_find_first_token: *first (device int64, pre-set to n by the caller) = index of the first `token` in the
  * flattened [B*L] ids, i.e. `(input_ids == id).nonzero()[0]`; left at n when absent.

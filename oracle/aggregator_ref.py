@@ -265,8 +265,9 @@ def aggregator_forward(s: State, images: torch.Tensor, cfg: AggregatorConfig, *,
     B, S, C_in, H, W = images.shape
     D = cfg.embed_dim
     images = images.float()
-    mean = torch.tensor(_RESNET_MEAN).view(1, 1, 3, 1, 1)
-    std = torch.tensor(_RESNET_STD).view(1, 1, 3, 1, 1)
+    dev = images.device   # the restatement is device-agnostic fp32 PyTorch: tests run the big cases with it on `cuda`
+    mean = torch.tensor(_RESNET_MEAN, device=dev).view(1, 1, 3, 1, 1)
+    std = torch.tensor(_RESNET_STD, device=dev).view(1, 1, 3, 1, 1)
     x = ((images - mean) / std).reshape(B * S, C_in, H, W)
     gh, gw = H // cfg.patch_size, W // cfg.patch_size
     n_special = cfg.patch_start_idx
@@ -276,8 +277,8 @@ def aggregator_forward(s: State, images: torch.Tensor, cfg: AggregatorConfig, *,
     reg = _special_tokens(s["register_token"], B, S)
     tokens = torch.cat([cam, reg, patch_tokens], dim=1)                            # [B*S, P, D]
     P = tokens.shape[1]
-    pos = token_positions(gh, gw, n_special)[None].expand(B * S, -1, -1)
-    tables = rope_tables(max(gh, gw), cfg.head_dim, cfg.rope_freq)
+    pos = token_positions(gh, gw, n_special).to(dev)[None].expand(B * S, -1, -1)
+    tables = tuple(t.to(dev) for t in rope_tables(max(gh, gw), cfg.head_dim, cfg.rope_freq))
 
     outs: List[torch.Tensor] = []
     for i in range(cfg.depth):

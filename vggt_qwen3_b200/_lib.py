@@ -186,6 +186,11 @@ _EXTRA_DECLS: dict[str, list] = {
     "vq_preprocess_geometry": [_i32, _i32, _i32, _vp],
     "vq_preprocess_taps": [_i32, _i32, _i32, _i32, _vp, _i64],
     "vq_preprocess_views": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, C.c_size_t, _vp],
+    "vq_geom_head_forward": [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                             _i32, _i32, _i32, _vp],
+    "vq_geom_head_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "vq_splice_features": [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp],
+    "vq_splice_features_backward": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp],
     "vq_find_first_token": [_vp, _i64, _i64, _vp, _vp],
     "vq_splice_insert": [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "vq_adamw_step": [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp],

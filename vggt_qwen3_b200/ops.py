@@ -195,6 +195,86 @@ def splice_overwrite(inputs_embeds: torch.Tensor, input_ids: torch.Tensor, featu
     return inputs_embeds
 
 
+def splice_features(inputs_embeds: torch.Tensor, input_ids: torch.Tensor, geom: Optional[torch.Tensor], n_geom: int,
+                    vis: torch.Tensor, image_id: int, overflow: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In-place training splice of `cat([geom.expand(n_geom), vis], 1)` over every <image> position without building
+    the span (src/models/vggt_qwen3_vlm.py:187-195): geom f32 [B, hidden] (or None), vis [B, n_vis, hidden]."""
+    if not inputs_embeds.is_cuda:
+        raise RuntimeError("splice_features: CUDA tensors only")
+    B, L, H = inputs_embeds.shape
+    assert inputs_embeds.is_contiguous() and input_ids.shape == (B, L) and vis.shape[0] == B and vis.shape[2] == H
+    ids = input_ids.to(torch.int64).contiguous()
+    v = vis.to(inputs_embeds.dtype).contiguous()
+    g = None
+    if geom is not None and n_geom > 0:
+        assert geom.shape == (B, H)
+        g = geom.to(torch.float32).contiguous()
+    _lib.check(
+        _lib.lib().vq_splice_features(inputs_embeds.data_ptr(), _dtype_code(inputs_embeds.dtype), ids.data_ptr(),
+                                      _ptr(g), n_geom if g is not None else 0, v.data_ptr(), v.shape[1], B, L, H,
+                                      int(image_id), _ptr(overflow), _stream()),
+        "vq_splice_features")
+    return inputs_embeds
+
+
+def splice_features_backward(grad: torch.Tensor, input_ids: torch.Tensor, n_geom: int, n_vis: int, image_id: int,
+                             need_embeds: bool = True, need_geom: bool = True, need_vis: bool = True):
+    """Backward of `splice_features`: (d_embeds [B,L,H] in grad's dtype, d_geom f32 [B,H], d_vis f32 [B,n_vis,H])."""
+    B, L, H = grad.shape
+    g = grad.contiguous()
+    ids = input_ids.to(torch.int64).contiguous()
+    d_emb = torch.empty_like(g) if need_embeds else None
+    d_geom = torch.empty(B, H, dtype=torch.float32, device=g.device) if (need_geom and n_geom > 0) else None
+    d_vis = torch.empty(B, n_vis, H, dtype=torch.float32, device=g.device) if need_vis else None
+    _lib.check(
+        _lib.lib().vq_splice_features_backward(g.data_ptr(), _dtype_code(g.dtype), ids.data_ptr(), _ptr(d_emb),
+                                               _ptr(d_geom), _ptr(d_vis), n_geom, n_vis, B, L, H, int(image_id),
+                                               _stream()),
+        "vq_splice_features_backward")
+    return d_emb, d_geom, d_vis
+
+
+def geom_head_forward(parts, widths, w1, b1, w2, b2, B: int, V: int):
+    """(y, pooled, pre, act) of encode_geom + geom_head (src/models/vggt_qwen3_vlm.py:51-56,164-177); `parts` = four f32
+    [B, V, widths[k]] tensors or None (zeros)."""
+    H, in_dim = w1.shape
+    dev = w1.device
+    for t in (w1, b1, w2, b2):
+        _req(t, torch.float32, "geom_head parameter")
+    keep = [None if p is None else p.to(device=dev, dtype=torch.float32).contiguous() for p in parts]
+    ptrs = (C.c_void_p * 4)(*[None if p is None else p.data_ptr() for p in keep])
+    wid = (C.c_int32 * 4)(*[int(w) for w in widths])
+    pooled = torch.empty(B, in_dim, dtype=torch.float32, device=dev)
+    pre = torch.empty(B, H, dtype=torch.float32, device=dev)
+    act = torch.empty(B, H, dtype=torch.float32, device=dev)
+    y = torch.empty(B, H, dtype=torch.float32, device=dev)
+    _lib.check(
+        _lib.lib().vq_geom_head_forward(ptrs, wid, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                        pooled.data_ptr(), pre.data_ptr(), act.data_ptr(), y.data_ptr(), B, V, in_dim, H,
+                                        _stream()),
+        "vq_geom_head_forward")
+    return y, pooled, pre, act
+
+
+def geom_head_backward(dy, pooled, pre, act, w2):
+    """(dw1, db1, dw2, db2) f32."""
+    B, H = dy.shape
+    in_dim = pooled.shape[1]
+    dev = dy.device
+    dy = dy.to(torch.float32).contiguous()
+    dw1 = torch.empty(H, in_dim, dtype=torch.float32, device=dev)
+    db1 = torch.empty(H, dtype=torch.float32, device=dev)
+    dw2 = torch.empty(H, H, dtype=torch.float32, device=dev)
+    db2 = torch.empty(H, dtype=torch.float32, device=dev)
+    scratch = torch.empty(B, H, dtype=torch.float32, device=dev)
+    _lib.check(
+        _lib.lib().vq_geom_head_backward(dy.data_ptr(), pooled.data_ptr(), pre.data_ptr(), act.data_ptr(), w2.data_ptr(),
+                                         dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(),
+                                         scratch.data_ptr(), B, in_dim, H, 0, _stream()),
+        "vq_geom_head_backward")
+    return dw1, db1, dw2, db2
+
+
 def splice_insert(inputs_embeds: torch.Tensor, attention_mask: torch.Tensor, input_ids: torch.Tensor,
                   vis_tokens: torch.Tensor, image_id: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """Inference splice (src/inference/qa_inference.py:119-145): the FIRST <image> token (in (batch, position) order)

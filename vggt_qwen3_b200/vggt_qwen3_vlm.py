@@ -135,28 +135,52 @@ class VGGTQwen3VLM(nn.Module):
         """The trainable half (reference :162): `self.projector(tokens)` under autograd."""
         return self.projector(tokens)
 
+    _GEOM_KEYS = (("R", "t"), ("t", "R"), ("K", "R"), ("depth_hist", "R"))   # (key, fallback shape donor), reference :168-173
+
+    def _geom_vector(self, geom_token: Optional[Dict[str, torch.Tensor]]) -> Optional[torch.Tensor]:
+        """geom_head(mean over views of cat(R, t, K, depth_hist)) -> f32 [B, hidden] (reference :164-176), on
+        libvq_b200.so (vq_geom_head_forward, differentiable w.r.t. the geom_head parameters); None when bypassed."""
+        if not geom_token or self.geom_tokens == 0:
+            return None
+        parts, widths = [], []
+        for key, like in self._GEOM_KEYS:
+            if key in geom_token:
+                parts.append(geom_token[key])
+                widths.append(geom_token[key].shape[-1])
+            else:   # the reference substitutes zeros shaped like another entry
+                parts.append(None)
+                widths.append(geom_token[like].shape[-1])
+        donor = next(p for p in parts if p is not None)
+        if donor.dim() != 3:
+            raise ValueError("geom_token entries must be [B, V, features]")
+        lin1, lin2 = self.geom_head[0], self.geom_head[2]
+        if sum(widths) != lin1.in_features:
+            raise RuntimeError(f"geom features have width {sum(widths)}, geom_head expects {lin1.in_features}")
+        return _GeomHeadFunction.apply(parts, widths, donor.shape[0], donor.shape[1], lin1.weight, lin1.bias,
+                                       lin2.weight, lin2.bias)
+
     def encode_geom(self, geom_token: Optional[Dict[str, torch.Tensor]]) -> Optional[torch.Tensor]:
         """[B, geom_tokens, hidden] from per-view (R 9 | t 3 | K 9 | depth_hist 16) features averaged over views
         (reference :164-177); None when there is no geometry input or geom_tokens == 0."""
-        if not geom_token or self.geom_tokens == 0:
+        y = self._geom_vector(geom_token)
+        if y is None:
             return None
-        parts = []
-        for key, like in (("R", "t"), ("t", "R"), ("K", "R"), ("depth_hist", "R")):
-            parts.append(geom_token[key] if key in geom_token else torch.zeros_like(geom_token[like]))
-        pooled = torch.cat(parts, dim=-1).mean(dim=1)
-        return self.geom_head(pooled).unsqueeze(1).expand(-1, self.geom_tokens, -1)
+        return y.to(self.geom_head[0].weight.dtype).unsqueeze(1).expand(-1, self.geom_tokens, -1)
 
     def build_inputs_embeds(self, images: torch.Tensor, geom_token, input_ids: torch.Tensor,
                             trainable_projector: bool = False) -> torch.Tensor:
-        """encode + splice: inputs_embeds with [geom, vis] written over every <image> position (:187-195)."""
+        """encode + splice: inputs_embeds with [geom, vis] written over every <image> position (:187-195).  The span
+        `cat([geom.expand(geom_tokens), vis], 1)` is never materialised: one vq_splice_features launch reads both."""
         vis = self.encode_images_trainable(images) if trainable_projector else self.encode_images(images)
-        geom = self.encode_geom(geom_token)
-        features = vis if geom is None else torch.cat([geom.to(vis.dtype), vis], dim=1)
+        geom = self._geom_vector(geom_token)
         inputs_embeds = self.text_model.get_input_embeddings()(input_ids)
         image_id = self.tokenizer.convert_tokens_to_ids("<image>")
-        if features.requires_grad or inputs_embeds.requires_grad:
-            return _SpliceFunction.apply(inputs_embeds, input_ids, features, image_id)
-        return ops.splice_overwrite(inputs_embeds.contiguous(), input_ids, features, image_id)
+        n_geom = self.geom_tokens if geom is not None else 0
+        needs_grad = torch.is_grad_enabled() and (vis.requires_grad or inputs_embeds.requires_grad or
+                                                  (geom is not None and geom.requires_grad))
+        if needs_grad:
+            return _SpliceFunction.apply(inputs_embeds, input_ids, geom, vis, image_id, n_geom)
+        return ops.splice_features(inputs_embeds.contiguous(), input_ids, geom, n_geom, vis, image_id)
 
     def forward(self, images, geom_token, input_ids, attention_mask, labels) -> torch.Tensor:
         inputs_embeds = self.build_inputs_embeds(images, geom_token, input_ids)
@@ -164,30 +188,46 @@ class VGGTQwen3VLM(nn.Module):
         return outputs.loss
 
 
-class _SpliceFunction(torch.autograd.Function):
-    """Differentiable splice: d(features) gathers the rows written, d(inputs_embeds) is zero there."""
+class _GeomHeadFunction(torch.autograd.Function):
+    """geom_head on the C ABI: forward vq_geom_head_forward, backward vq_geom_head_backward (parameter gradients only:
+    the geometry features are data)."""
 
     @staticmethod
-    def forward(ctx, inputs_embeds, input_ids, features, image_id):
+    def forward(ctx, parts, widths, B, V, w1, b1, w2, b2):
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        y, pooled, pre, act = ops.geom_head_forward([None if p is None else p.detach() for p in parts], widths,
+                                                    f32(w1), f32(b1), f32(w2), f32(b2), B, V)
+        ctx.save_for_backward(pooled, pre, act, w2)
+        ctx.dtypes = (w1.dtype, b1.dtype, w2.dtype, b2.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        pooled, pre, act, w2 = ctx.saved_tensors
+        grads = ops.geom_head_backward(dy, pooled, pre, act, w2.detach().to(torch.float32).contiguous())
+        return (None, None, None, None, *[g.to(dt) for g, dt in zip(grads, ctx.dtypes)])
+
+
+class _SpliceFunction(torch.autograd.Function):
+    """Differentiable fused splice: forward vq_splice_features on a copy of inputs_embeds, backward
+    vq_splice_features_backward (one launch: written rows route their gradient to the feature they came from and are
+    zeroed in d(inputs_embeds)); no host synchronisation in either direction."""
+
+    @staticmethod
+    def forward(ctx, inputs_embeds, input_ids, geom, vis, image_id, n_geom):
         out = inputs_embeds.detach().clone().contiguous()
-        ops.splice_overwrite(out, input_ids, features.detach(), image_id)
+        ops.splice_features(out, input_ids, None if geom is None else geom.detach(), n_geom, vis.detach(), image_id)
         ctx.save_for_backward(input_ids)
-        ctx.image_id, ctx.n = image_id, features.shape[1]
-        ctx.feat_dtype = features.dtype
+        ctx.image_id, ctx.n_geom, ctx.n_vis = image_id, n_geom, vis.shape[1]
+        ctx.vis_dtype = vis.dtype
+        ctx.has_geom = geom is not None
         return out
 
     @staticmethod
     def backward(ctx, grad):
         (input_ids,) = ctx.saved_tensors
-        B, L = input_ids.shape
-        n = ctx.n
-        # row r of sample b was written from features[b, r - pos] where pos is the last <image> position in (r-n, r]
-        is_img = input_ids == ctx.image_id
-        idx = torch.arange(L, device=grad.device).expand(B, L)
-        last = torch.cummax(torch.where(is_img, idx, torch.full_like(idx, -1)), dim=1).values
-        written = (last >= 0) & (idx - last < n)
-        g_feat = torch.zeros(B, n, grad.shape[-1], device=grad.device, dtype=torch.float32)
-        b_idx, r_idx = written.nonzero(as_tuple=True)
-        g_feat.index_put_((b_idx, (idx - last)[b_idx, r_idx]), grad[b_idx, r_idx].float(), accumulate=True)
-        g_emb = grad.masked_fill(written.unsqueeze(-1), 0)
-        return g_emb, None, g_feat.to(ctx.feat_dtype), None
+        need_emb, _, need_geom, need_vis = ctx.needs_input_grad[:4]
+        d_emb, d_geom, d_vis = ops.splice_features_backward(
+            grad, input_ids, ctx.n_geom, ctx.n_vis, ctx.image_id, need_embeds=need_emb,
+            need_geom=need_geom and ctx.has_geom, need_vis=need_vis)
+        return (d_emb, None, d_geom, None if d_vis is None else d_vis.to(ctx.vis_dtype), None, None)
