@@ -251,6 +251,15 @@ int vq_preprocess_views(const uint8_t* views_hwc, float* out_chw, int32_t frames
 int vq_adamw_step(float* param, float* exp_avg, float* exp_avg_sq, const void* grad, int32_t grad_dtype,
                   void* param_bf16, int64_t n, int32_t step, float lr, float beta1, float beta2, float eps,
                   float weight_decay, float grad_scale, vq_stream_t stream);
+/* f3, sharded (ZeRO-1 style; the reference's equivalent is DeepSpeed's reduce-scatter / all-gather,
+ * configs/deepspeed_zero3.json:7-14): the reduce step of a reduce-scatter fused into the optimizer.  The gradient of
+ * the n elements this rank owns is the SUM of n_srcs (1..16) sources of the same dtype -- this rank's shard plus the
+ * peers' shards pulled over NVLink -- accumulated in fp32 and never written back; AdamW as above on the f32 master
+ * shard; weight_out (optional, bf16 or f32) receives the updated compute copy the forward kernels read and the peers
+ * all-gather.  n may be any positive count (scalar tail handled). */
+int vq_adamw_reduce_step(float* param, float* exp_avg, float* exp_avg_sq, const void* const* grad_srcs, int32_t n_srcs,
+                         int32_t grad_dtype, void* weight_out, int32_t weight_dtype, int64_t n, int32_t step, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float grad_scale, vq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * vq_aggregator_forward — the whole frozen VGGT Aggregator forward (csrc/aggregator.cu): replaces
@@ -390,18 +399,30 @@ typedef struct vq_perceiver_weights {
   const float* out_proj_b;
 } vq_perceiver_weights;
 
-/* f32 gradient destinations, same shapes as the parameters.  Every buffer is OVERWRITTEN unless accumulate != 0. */
+/* Gradient destinations, same shapes as the parameters.  Every buffer is OVERWRITTEN unless accumulate != 0.
+ * Matrix gradients (the *_w of the Linear layers, produced by the wgrad GEMMs) are f32 or -- weight_grad_bf16 = 1 --
+ * bf16 written straight from the fp32 TMEM accumulators (the wire format of the data-parallel reduce: no f32 gradient
+ * buffer, no cast pass); vectors (biases, LayerNorm affine) and the latents are always f32. */
 typedef struct vq_perceiver_layer_grads {
-  float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b, *norm1_w, *norm1_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b,
-      *norm2_w, *norm2_b;
+  void* in_proj_w;
+  float* in_proj_b;
+  void* out_proj_w;
+  float *out_proj_b, *norm1_w, *norm1_b;
+  void* fc1_w;
+  float* fc1_b;
+  void* fc2_w;
+  float *fc2_b, *norm2_w, *norm2_b;
 } vq_perceiver_layer_grads;
 
 typedef struct vq_perceiver_grads {
   float* latents;
-  float *in_proj_w, *in_proj_b;
+  void* in_proj_w;
+  float* in_proj_b;
   const vq_perceiver_layer_grads* layers;
-  float *out_proj_w, *out_proj_b;
+  void* out_proj_w;
+  float* out_proj_b;
   int32_t accumulate;
+  int32_t weight_grad_bf16; /* 0: matrix gradients f32, 1: bf16 */
 } vq_perceiver_grads;
 
 /* Called on the host right after the work producing the gradients of `layer` has been ENQUEUED

@@ -86,8 +86,19 @@ def test_new_entry_points_validate_arguments_without_gpu():
     assert b"null pointer" in h.vq_last_error()
     buf = (ctypes.c_float * 16)()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    assert h.vq_adamw_step(p, p, p, p, 0, None, 6, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
-    assert b"multiple of 4" in h.vq_last_error()
+    assert h.vq_adamw_step(p, p, p, p, 0, None, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
+    assert b"must be positive" in h.vq_last_error()
+    assert h.vq_adamw_step(p, p, p, p, 0, None, 8, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0.0, None) == -1
+    assert b"grad_scale" in h.vq_last_error()          # a zero scale is an error, not silently 1
+    srcs = (ctypes.c_void_p * 2)(p, p)
+    assert h.vq_adamw_reduce_step(p, p, p, srcs, 17, 0, None, 0, 8, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
+    assert b"gradient sources" in h.vq_last_error()
+    assert h.vq_geom_head_forward(None, None, None, None, None, None, None, None, None, None, 1, 1, 37, 64, None) == -1
+    assert h.vq_splice_features(None, 0, None, None, 0, None, 4, 1, 8, 64, 7, None, None) == -1
+    d = _lib.DropoutDesc(); d.p = 1.5
+    keep = (ctypes.c_uint8 * 64)()
+    assert h.vq_dropout_mask(ctypes.cast(keep, ctypes.c_void_p), 8, 8, 8, ctypes.byref(d), None) == -1
+    assert b"dropout p" in h.vq_last_error()
     assert h.vq_adamw_step(p, p, p, p, 0, None, 8, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
     assert b"step counts from 1" in h.vq_last_error()
     assert h.vq_splice_insert(None, 0, None, 8, None, None, None, None, 1, 8, 64, 4, None) == -1

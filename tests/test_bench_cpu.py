@@ -15,8 +15,12 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_reference_arm_prints_the_contract_line():
-    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "4", "--warmup", "2"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    import os
+
+    # every reference step is one full-depth scene (tens of seconds of CPU work here): one step, bounded budget
+    env = dict(os.environ, VQ_REF_BUDGET_S="30")
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -26,6 +30,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["config"]["workload"].startswith("c2")
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert "full depth" in cb["sample"] and cb["steps_executed"] >= 1
+    # ms_per_step is the time of an EXECUTED step (one scene), consistent with the run's wall clock
+    assert d["ms_per_step"] * cb["steps_executed"] / 1e3 <= d["wall_seconds"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

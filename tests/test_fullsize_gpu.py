@@ -33,8 +33,9 @@ def _attention_reference(qkv, n_seq, L, heads, chunk=2048):
             k = qkv[rows, HD + h * 64:HD + (h + 1) * 64].float()
             v = qkv[rows, 2 * HD + h * 64:2 * HD + (h + 1) * 64].float()
             for c in range(0, L, chunk):
-                sc = (q[c:c + chunk] @ k.t()) * math.log(2.0)
-                out[s * L + c:s * L + c + chunk, h * 64:(h + 1) * 64] = torch.softmax(sc, dim=-1) @ v
+                e = min(L, c + chunk)
+                sc = (q[c:e] @ k.t()) * math.log(2.0)
+                out[s * L + c:s * L + e, h * 64:(h + 1) * 64] = torch.softmax(sc, dim=-1) @ v
     return out
 
 
@@ -142,17 +143,25 @@ def _probe(t: torch.Tensor, index: int, n_probes=4, n_sample=4096):
     return np.concatenate([np.array(out), flat[::stride][:n_sample].numpy()])
 
 
-def _check_probe(got: np.ndarray, ref: np.ndarray, what: str, tol=3e-2):
+def _check_probe(got: np.ndarray, ref: np.ndarray, what: str, tol=5e-2):
+    """bf16 tensor-core backward through six layers against the fp32 reference: relative L2 error <= 5e-2 and cosine
+    >= 0.999 on the strided sample (a cosine of 0.999 is a relative error of 4.5e-2); the +-1 projections of the
+    error are sums with standard deviation |error|, so they are bounded at three times that."""
     norm = ref[0]
     assert abs(got[0] - norm) <= tol * norm, f"{what}: norm {got[0]:.6e} vs {norm:.6e}"
-    # a +-1 projection of the error has the size of the error's norm: bound it by tol * |g|
     for k in range(1, 5):
-        assert abs(got[k] - ref[k]) <= tol * norm, f"{what}: probe {k}: {got[k]:.6e} vs {ref[k]:.6e} (norm {norm:.3e})"
+        assert abs(got[k] - ref[k]) <= 3 * tol * norm, f"{what}: probe {k}: {got[k]:.6e} vs {ref[k]:.6e} (norm {norm:.3e})"
     a, b = torch.from_numpy(got[5:]), torch.from_numpy(ref[5:])
+    rel, cos = 0.0, 1.0
     if b.norm() > 0:
         rel = ((a - b).norm() / b.norm()).item()
         cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
-        assert rel <= tol and cos >= 0.999, f"{what}: sample rel L2 {rel:.3e}, cosine {cos:.6f}"
+    _ERRORS.append(f"{what:50s} sample rel L2 {rel:.3e} cosine {cos:.6f} probe err/norm "
+                   f"{max(abs(got[k] - ref[k]) for k in range(1, 5)) / max(norm, 1e-30):.3e}")
+    assert rel <= tol and cos >= 0.999, f"{what}: sample rel L2 {rel:.3e}, cosine {cos:.6f}"
+
+
+_ERRORS = []
 
 
 def test_full_size_perceiver_forward_backward_vs_reference_class():
@@ -178,5 +187,10 @@ def test_full_size_perceiver_forward_backward_vs_reference_class():
     assert_token_parity(got_rows, ref_rows, "full-size perceiver output rows")
     _check_probe(_probe(out, 0), z["out"], "output")
     _check_probe(_probe(tok.grad, 1), z["grad_tokens"], "grad tokens")
-    for i, (n, p) in enumerate(m.named_parameters()):
-        _check_probe(_probe(p.grad, 2 + i), z["grad/" + n], f"grad {n}")
+    try:
+        for i, (n, p) in enumerate(m.named_parameters()):
+            _check_probe(_probe(p.grad, 2 + i), z["grad/" + n], f"grad {n}")
+    finally:   # per-tensor error table for profiles/ (only where the scratch directory exists)
+        out_dir = Path(__file__).resolve().parent.parent / "gpurun_out"
+        if out_dir.is_dir():
+            (out_dir / "perceiver_full_errors.txt").write_text("\n".join(_ERRORS) + "\n")

@@ -114,3 +114,78 @@ def test_fused_adamw_refreshes_projector_compute_copies():
     assert (yb - y0).abs().max() > 1e-3, "the step did not change the output"
     changed = [k for k, v in b.state_dict().items() if not torch.equal(v, before[k])]
     assert len(changed) == len(before), "every parameter (matrices AND vectors) must have been updated"
+
+
+@pytest.mark.parametrize("n,n_srcs,gdtype,wdtype", [
+    (1 << 16, 1, torch.float32, torch.bfloat16), (4099, 3, torch.bfloat16, torch.bfloat16),
+    (128 * 1000, 8, torch.bfloat16, torch.float32), (7, 2, torch.float32, torch.float32)])
+def test_adamw_reduce_step_sums_sources_in_fp32(n, n_srcs, gdtype, wdtype):
+    """vq_adamw_reduce_step: the gradient is the fp32 SUM of the sources (never rounded back to bf16 between adds),
+    AdamW on the f32 master slice, compute copy written in the same pass; any n (scalar tail)."""
+    from vggt_qwen3_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n + n_srcs)
+    p = torch.randn(n, device="cuda", generator=g)
+    ref_p = torch.nn.Parameter(p.clone())
+    ref = torch.optim.AdamW([ref_p], lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.1)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    w = torch.empty(n, device="cuda", dtype=wdtype)
+    for step in range(1, 4):
+        srcs = [(torch.randn(n, device="cuda", generator=g) * (10.0 ** (i % 3))).to(gdtype) for i in range(n_srcs)]
+        ref_p.grad = torch.stack([s.double() for s in srcs]).sum(0).float() / n_srcs
+        ref.step()
+        ops.adamw_reduce_step(p, m, v, srcs, w, step, lr=1e-2, betas=(0.9, 0.99), weight_decay=0.1, grad_scale=1.0 / n_srcs)
+    assert torch.allclose(p, ref_p.detach(), rtol=3e-5, atol=3e-6), (p - ref_p.detach()).abs().max()
+    assert torch.equal(w, p.to(wdtype))
+    with pytest.raises(RuntimeError):
+        ops.adamw_reduce_step(p, m, v, srcs, w, 4, lr=1e-2, grad_scale=0.0)
+
+
+@pytest.mark.parametrize("accumulate", [1, 2])
+def test_sharded_adamw_single_gpu_training_steps(accumulate):
+    """ShardedAdamW at world size 1 on the real kernels: bf16 wire gradients written by the wgrad GEMMs (or the f32
+    accumulation buffer cast at the boundary), flat single-launch AdamW, compute copies updated in place.  Reference:
+    the fp32 oracle's gradients through torch.optim.AdamW.  Adam normalises the gradient, so bf16 gradient error moves
+    a first step by at most a few per cent of its size."""
+    from vggt_qwen3_b200.optim import ShardedAdamW
+    from vggt_qwen3_b200.projector_perceiver import PerceiverConfig, PerceiverProjector
+
+    shape = P.PerceiverShape(256, 64, 2, 2, 512, 0.0, 128, 192)
+    state = P.init_perceiver_state(shape, seed=0, nonzero_bias=True)
+    state["latents"] = state["latents"] * 25.0
+    m = PerceiverProjector(PerceiverConfig(256, 64, 2, 2, 512, 0.0), in_dim=128, out_dim=192)
+    m.load_state_dict(state, strict=True)
+    m = m.cuda().eval()
+    opt = ShardedAdamW(m, lr=1e-3, weight_decay=0.01, accumulate_steps=accumulate)
+    ref_state = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    ref_opt = torch.optim.AdamW(list(ref_state.values()), lr=1e-3, weight_decay=0.01)
+    g = torch.Generator().manual_seed(3)
+    for step in range(3):
+        ref_opt.zero_grad()
+        opt.zero_grad()
+        for micro in range(accumulate):
+            tokens = torch.randn(2, 64, shape.in_dim, generator=g)
+            grad_out = torch.randn(2, shape.num_latents, shape.out_dim, generator=g)
+            out = P.perceiver_forward(ref_state, tokens, shape.num_heads)
+            out.backward(grad_out / accumulate)
+            y = m(tokens.cuda())
+            y.backward(grad_out.cuda())
+            assert all(p.grad is None for p in m.parameters()) or accumulate > 1
+        ref_opt.step()
+        opt.step()
+    opt.sync_parameters()
+    for name, p in m.named_parameters():
+        r, p0 = ref_state[name].detach(), state[name]
+        moved = (r - p0).norm()
+        err = (p.detach().cpu() - r).norm()
+        assert err <= 0.08 * moved + 1e-7, f"{name}: update error {err:.3e} vs update size {moved:.3e}"
+    # the next forward reads the updated compute copies: same output as a fresh module loaded from the synced parameters
+    x = torch.randn(2, 64, shape.in_dim, generator=g).cuda()
+    fresh = PerceiverProjector(PerceiverConfig(256, 64, 2, 2, 512, 0.0), in_dim=128, out_dim=192).cuda().eval()
+    fresh.load_state_dict(m.state_dict())
+    assert torch.equal(m(x).detach(), fresh(x).detach())
+    # load_state_dict on the module is picked up by the optimizer (masters + compute copies reloaded)
+    m.load_state_dict(state)
+    y_loaded = m(x).detach()
+    fresh.load_state_dict(state)
+    assert torch.equal(y_loaded, fresh(x).detach())

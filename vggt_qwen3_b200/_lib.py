@@ -135,7 +135,7 @@ class PerceiverGrads(C.Structure):
         ("latents", C.c_void_p), ("in_proj_w", C.c_void_p), ("in_proj_b", C.c_void_p),
         ("layers", C.POINTER(PerceiverLayerGrads)),
         ("out_proj_w", C.c_void_p), ("out_proj_b", C.c_void_p),
-        ("accumulate", C.c_int32),
+        ("accumulate", C.c_int32), ("weight_grad_bf16", C.c_int32),
     ]
 
 
@@ -194,6 +194,8 @@ _EXTRA_DECLS: dict[str, list] = {
     "vq_find_first_token": [_vp, _i64, _i64, _vp, _vp],
     "vq_splice_insert": [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "vq_adamw_step": [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp],
+    "vq_adamw_reduce_step": [_vp, _vp, _vp, C.POINTER(C.c_void_p), _i32, _i32, _vp, _i32, _i64, _i32, _f32, _f32, _f32,
+                             _f32, _f32, _f32, _vp],
     "vq_softmax_fwd": [_vp, _vp, _i64, _i32, _i32, _i32, C.POINTER(DropoutDesc), _vp, _vp],
     "vq_softmax_bwd": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, C.POINTER(DropoutDesc), _vp],
     "vq_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, C.POINTER(DropoutDesc), _vp, _vp],

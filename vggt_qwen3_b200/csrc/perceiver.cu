@@ -260,10 +260,13 @@ extern "C" int vq_perceiver_backward(const vq_perceiver_cfg* c, const vq_perceiv
   const float scale = 1.0f / sqrtf((float)d.hd);
   const int acc = gr->accumulate;
 
-  // f32 wgrad: dW[N_out, K_in] (+)= dY^T X, both operands MN-major over the row (contraction) dimension
-  auto wgrad = [&](float* dW, int n_out, int k_in, const void* dY, long long lddy, const void* X, long long ldx,
+  // wgrad: dW[N_out, K_in] (+)= dY^T X, both operands MN-major over the row (contraction) dimension; f32, or bf16
+  // straight from the fp32 accumulators when the caller reduces / steps on bf16 gradients
+  const int wdt = gr->weight_grad_bf16 ? VQ_BF16 : VQ_F32;
+  const size_t welt = gr->weight_grad_bf16 ? 2 : 4;
+  auto wgrad = [&](void* dW, int n_out, int k_in, const void* dY, long long lddy, const void* X, long long ldx,
                    int rows) {
-    return gemm(st, n_out, k_in, rows, dY, lddy, 1, X, ldx, 1, dW, k_in, VQ_F32, nullptr, acc ? dW : nullptr, k_in);
+    return gemm(st, n_out, k_in, rows, dY, lddy, 1, X, ldx, 1, dW, k_in, wdt, nullptr, acc ? dW : nullptr, k_in);
   };
   // bias / LN-affine gradients are accumulated by the kernels: clear them first unless accumulating
   auto clear = [&](float* p, size_t n) -> int {
@@ -353,7 +356,7 @@ extern "C" int vq_perceiver_backward(const vq_perceiver_cfg* c, const vq_perceiv
     }
     // projections: in_proj_weight.grad rows [0:E] <- q, rows [E:3E] <- k,v
     RUN(wgrad(lg.in_proj_w, E, E, k.dq, E, s.lat[l], E, R));
-    RUN(wgrad(lg.in_proj_w + (size_t)E * E, 2 * E, E, k.dkv, 2 * E, s.ctx, E, C));
+    RUN(wgrad(reinterpret_cast<char*>(lg.in_proj_w) + (size_t)E * E * welt, 2 * E, E, k.dkv, 2 * E, s.ctx, E, C));
     RUN(clear(lg.in_proj_b, 3 * (size_t)E));
     RUN(vq_colsum(k.dq, VQ_BF16, lg.in_proj_b, R, E, E, st));
     RUN(vq_colsum(k.dkv, VQ_BF16, lg.in_proj_b + E, C, 2 * E, 2 * E, st));

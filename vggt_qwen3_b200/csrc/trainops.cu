@@ -64,44 +64,76 @@ splice_insert_kernel(const T* __restrict__ emb, const M* __restrict__ mask, cons
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, grad_scale, bc1, bc2_sqrt;
 };
+constexpr int kMaxGradSources = 16;
+struct GradSources {
+  const void* src[kMaxGradSources];   // same dtype, same length: the gradient is their sum (accumulated in fp32)
+  int n;
+};
 
-template <bool GRAD_BF16>
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamArgs& a, float decay,
+                                            float step) {
+  g *= a.grad_scale;
+  m = a.beta1 * m + (1.0f - a.beta1) * g;
+  v = a.beta2 * v + (1.0f - a.beta2) * g * g;
+  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+  p = p * decay - step * (m / denom);
+}
+
+// GRAD_BF16: dtype of the gradient sources; W_BF16: dtype of the optional compute copy (bf16 for matrices, f32 for the
+// vectors the kernels read in f32).  With more than one source this is the reduce step of a reduce-scatter fused into
+// the optimizer: the shard of every rank's gradient (pulled over NVLink into local staging, or read from peer-mapped
+// memory) is summed in fp32 and never written back.
+template <bool GRAD_BF16, bool W_BF16>
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const void* __restrict__ grad,
-             __nv_bfloat16* __restrict__ p_bf16, long long n4, AdamArgs a) {
+adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const GradSources gs,
+             void* __restrict__ w_out, long long n, AdamArgs a) {
   const float decay = 1.0f - a.lr * a.weight_decay;
   const float step = a.lr / a.bc1;
+  const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<const float4*>(p)[i];
     float4 mm = reinterpret_cast<const float4*>(m)[i];
     float4 vv = reinterpret_cast<const float4*>(v)[i];
-    float g[4];
-    if constexpr (GRAD_BF16) {
-      const uint2 u = reinterpret_cast<const uint2*>(grad)[i];
-      g[0] = bf16_lo(u.x); g[1] = bf16_hi(u.x); g[2] = bf16_lo(u.y); g[3] = bf16_hi(u.y);
-    } else {
-      const float4 gg = reinterpret_cast<const float4*>(grad)[i];
-      g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < gs.n; ++s) {
+      if constexpr (GRAD_BF16) {
+        const uint2 u = reinterpret_cast<const uint2*>(gs.src[s])[i];
+        g[0] += bf16_lo(u.x); g[1] += bf16_hi(u.x); g[2] += bf16_lo(u.y); g[3] += bf16_hi(u.y);
+      } else {
+        const float4 gg = reinterpret_cast<const float4*>(gs.src[s])[i];
+        g[0] += gg.x; g[1] += gg.y; g[2] += gg.z; g[3] += gg.w;
+      }
     }
-    float* pe = &pp.x;
-    float* me = &mm.x;
-    float* ve = &vv.x;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gk = g[k] * a.grad_scale;
-      me[k] = a.beta1 * me[k] + (1.0f - a.beta1) * gk;
-      ve[k] = a.beta2 * ve[k] + (1.0f - a.beta2) * gk * gk;
-      const float denom = sqrtf(ve[k]) / a.bc2_sqrt + a.eps;
-      pe[k] = pe[k] * decay - step * (me[k] / denom);
-    }
+    adam_update(pp.x, mm.x, vv.x, g[0], a, decay, step);
+    adam_update(pp.y, mm.y, vv.y, g[1], a, decay, step);
+    adam_update(pp.z, mm.z, vv.z, g[2], a, decay, step);
+    adam_update(pp.w, mm.w, vv.w, g[3], a, decay, step);
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
-    if (p_bf16) {
-      uint2 o;
-      o.x = pack_bf16x2(pp.x, pp.y);
-      o.y = pack_bf16x2(pp.z, pp.w);
-      reinterpret_cast<uint2*>(p_bf16)[i] = o;
+    if (w_out) {
+      if constexpr (W_BF16) {
+        uint2 o;
+        o.x = pack_bf16x2(pp.x, pp.y);
+        o.y = pack_bf16x2(pp.z, pp.w);
+        reinterpret_cast<uint2*>(w_out)[i] = o;
+      } else {
+        reinterpret_cast<float4*>(w_out)[i] = pp;
+      }
+    }
+  }
+  // scalar tail (n % 4 elements), one thread
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (long long i = n4 << 2; i < n; ++i) {
+      float g = 0.f;
+      for (int s = 0; s < gs.n; ++s)
+        g += GRAD_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gs.src[s])[i])
+                       : reinterpret_cast<const float*>(gs.src[s])[i];
+      adam_update(p[i], m[i], v[i], g, a, decay, step);
+      if (w_out) {
+        if constexpr (W_BF16) reinterpret_cast<__nv_bfloat16*>(w_out)[i] = __float2bfloat16(p[i]);
+        else reinterpret_cast<float*>(w_out)[i] = p[i];
+      }
     }
   }
 }
@@ -161,36 +193,64 @@ extern "C" int vq_splice_insert(const void* inputs_embeds, int32_t dtype, const 
   return VQ_OK;
 }
 
-extern "C" int vq_adamw_step(float* param, float* exp_avg, float* exp_avg_sq, const void* grad, int32_t grad_dtype,
-                             void* param_bf16, int64_t n, int32_t step, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, float grad_scale, vq_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  VQ_CHECK_ARG(param && exp_avg && exp_avg_sq && grad, "null pointer");
-  VQ_CHECK_ARG(n > 0 && n % 4 == 0, "element count must be a positive multiple of 4");
+static int adamw_launch(float* param, float* exp_avg, float* exp_avg_sq, const void* const* grad_srcs, int n_srcs,
+                        int grad_dtype, void* weight_out, int weight_dtype, long long n, int step, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, float grad_scale, cudaStream_t stream) {
+  VQ_CHECK_ARG(param && exp_avg && exp_avg_sq && grad_srcs, "null pointer");
+  VQ_CHECK_ARG(n > 0, "element count must be positive");
+  VQ_CHECK_ARG(n_srcs >= 1 && n_srcs <= kMaxGradSources, "1..16 gradient sources");
   VQ_CHECK_ARG(step >= 1, "step counts from 1");
   VQ_CHECK_ARG(grad_dtype == VQ_F32 || grad_dtype == VQ_BF16, "grad dtype");
+  VQ_CHECK_ARG(weight_dtype == VQ_F32 || weight_dtype == VQ_BF16, "weight copy dtype");
+  VQ_CHECK_ARG(grad_scale != 0.f && grad_scale == grad_scale, "grad_scale must be a non-zero number");
   VQ_CHECK_ARG(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(exp_avg) |
                  reinterpret_cast<uintptr_t>(exp_avg_sq)) % 16) == 0,
                "param / state 16-byte alignment");
-  VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(grad) % (grad_dtype == VQ_F32 ? 16 : 8)) == 0, "grad alignment");
-  VQ_CHECK_ARG(!param_bf16 || (reinterpret_cast<uintptr_t>(param_bf16) % 8) == 0, "bf16 copy alignment");
+  GradSources gs;
+  gs.n = n_srcs;
+  for (int i = 0; i < n_srcs; ++i) {
+    VQ_CHECK_ARG(grad_srcs[i] && (reinterpret_cast<uintptr_t>(grad_srcs[i]) % (grad_dtype == VQ_F32 ? 16 : 8)) == 0,
+                 "gradient source alignment");
+    gs.src[i] = grad_srcs[i];
+  }
+  VQ_CHECK_ARG(!weight_out || (reinterpret_cast<uintptr_t>(weight_out) % (weight_dtype == VQ_F32 ? 16 : 8)) == 0,
+               "weight copy alignment");
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
-  a.grad_scale = grad_scale == 0.f ? 1.f : grad_scale;
+  a.grad_scale = grad_scale;
   a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-  const long long n4 = n / 4;
+  const long long n4 = n / 4 > 0 ? n / 4 : 1;
   const int sms = num_sms() > 0 ? num_sms() : 148;
   long long blocks = (n4 + 255) / 256;
   if (blocks > 8LL * sms) blocks = 8LL * sms;   // grid-stride: 8 resident CTAs of 256 threads per SM
-  const double bytes = (double)n * (12.0 + (grad_dtype == VQ_F32 ? 4.0 : 2.0) + 12.0 + (param_bf16 ? 2.0 : 0.0));
-  LaunchScope scope(kKindRow, "adamw_step", 1, 0, 0, 0, bytes, stream);
-  if (grad_dtype == VQ_BF16)
-    adamw_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(param, exp_avg, exp_avg_sq, grad,
-                                                             reinterpret_cast<__nv_bfloat16*>(param_bf16), n4, a);
-  else
-    adamw_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(param, exp_avg, exp_avg_sq, grad,
-                                                              reinterpret_cast<__nv_bfloat16*>(param_bf16), n4, a);
+  const double gbytes = grad_dtype == VQ_F32 ? 4.0 : 2.0, wbytes = !weight_out ? 0.0 : weight_dtype == VQ_F32 ? 4.0 : 2.0;
+  LaunchScope scope(kKindRow, n_srcs > 1 ? "adamw_reduce_step" : "adamw_step", n_srcs, 0, 0, 0,
+                    (double)n * (24.0 + gbytes * n_srcs + wbytes), stream);
+#define VQ_ADAM(G, W) \
+  adamw_kernel<G, W><<<(unsigned)blocks, 256, 0, stream>>>(param, exp_avg, exp_avg_sq, gs, weight_out, n, a)
+  if (grad_dtype == VQ_BF16) {
+    if (weight_dtype == VQ_BF16) VQ_ADAM(true, true); else VQ_ADAM(true, false);
+  } else {
+    if (weight_dtype == VQ_BF16) VQ_ADAM(false, true); else VQ_ADAM(false, false);
+  }
+#undef VQ_ADAM
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
+}
+
+extern "C" int vq_adamw_step(float* param, float* exp_avg, float* exp_avg_sq, const void* grad, int32_t grad_dtype,
+                             void* param_bf16, int64_t n, int32_t step, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, float grad_scale, vq_stream_t stream_) {
+  const void* srcs[1] = {grad};
+  return adamw_launch(param, exp_avg, exp_avg_sq, srcs, 1, grad_dtype, param_bf16, VQ_BF16, n, step, lr, beta1, beta2, eps,
+                      weight_decay, grad_scale, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vq_adamw_reduce_step(float* param, float* exp_avg, float* exp_avg_sq, const void* const* grad_srcs,
+                                    int32_t n_srcs, int32_t grad_dtype, void* weight_out, int32_t weight_dtype, int64_t n,
+                                    int32_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                    float grad_scale, vq_stream_t stream_) {
+  return adamw_launch(param, exp_avg, exp_avg_sq, grad_srcs, n_srcs, grad_dtype, weight_out, weight_dtype, n, step, lr,
+                      beta1, beta2, eps, weight_decay, grad_scale, reinterpret_cast<cudaStream_t>(stream_));
 }

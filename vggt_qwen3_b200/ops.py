@@ -322,6 +322,39 @@ def adamw_step(param: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Ten
         "vq_adamw_step")
 
 
+def adamw_reduce_step(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, grad_srcs, weight_out, step: int,
+                      *, lr: float, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+                      grad_scale: float = 1.0) -> None:
+    """AdamW on a flat f32 master slice whose gradient is the fp32 SUM of `grad_srcs` (1..16 equally long bf16 or f32
+    tensors: this rank's slice + the peers' slices); `weight_out` (bf16 or f32, optional) receives the updated compute
+    copy.  The reduce step of a reduce-scatter fused into the optimizer (vq_adamw_reduce_step)."""
+    for t, name in ((master, "master"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, name)
+    n = master.numel()
+    gdt = grad_srcs[0].dtype
+    for g in grad_srcs:
+        if not g.is_cuda or g.dtype != gdt or g.numel() != n or not g.is_contiguous():
+            raise RuntimeError("adamw_reduce_step: gradient sources must be contiguous CUDA tensors of one dtype and length")
+    ptrs = (C.c_void_p * len(grad_srcs))(*[g.data_ptr() for g in grad_srcs])
+    wdt = VQ_BF16
+    if weight_out is not None:
+        assert weight_out.numel() == n and weight_out.is_contiguous()
+        wdt = _dtype_code(weight_out.dtype)
+    _lib.check(
+        _lib.lib().vq_adamw_reduce_step(master.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), ptrs,
+                                        len(grad_srcs), _dtype_code(gdt), _ptr(weight_out), wdt, n, int(step), lr,
+                                        betas[0], betas[1], eps, weight_decay, grad_scale, _stream()),
+        "vq_adamw_reduce_step")
+
+
+def cast_f32_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst (bf16) = src (f32), flat contiguous CUDA tensors of equal length."""
+    _req(src, torch.float32, "src")
+    _req(dst, torch.bfloat16, "dst")
+    assert src.numel() == dst.numel() and src.is_contiguous() and dst.is_contiguous()
+    _lib.check(_lib.lib().vq_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "vq_cast_f32_bf16")
+
+
 def preprocess_views(views_u8: torch.Tensor, image_size: int) -> torch.Tensor:
     """`build_default_transform(image_size)` (src/dataio/collate_multiview.py:12-19) on a batch of equally sized RGB
     views: uint8 [..., H, W, 3] on the GPU -> float32 [..., 3, image_size, image_size] in [0, 1], bit-exact with

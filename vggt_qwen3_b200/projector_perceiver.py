@@ -94,7 +94,13 @@ class PerceiverProjector(nn.Module):
         self._compute: Optional[dict] = None
         self._grad_flat: Optional[torch.Tensor] = None
         self._grad_view_list: Optional[List[torch.Tensor]] = None
-        self._buffers: dict = {}   # (kind, nbytes, device) -> persistent uint8 scratch
+        self._flat_weights = None       # (bf16 matrices, f32 vectors) flat compute-copy storage, see use_flat_storage
+        self._flat_grads = None         # (matrices, vectors, views) flat gradient storage owned by an optimizer
+        self._flat_grads_fresh = True   # next backward overwrites the owned gradient storage (else accumulates)
+        # called (no arguments) at the top of every forward: lets an asynchronous optimizer make the current stream
+        # wait for the weight update / all-gather it still has in flight
+        self.before_forward: Optional[Callable[[], None]] = None
+        self._scratch_bufs: dict = {}   # (kind, nbytes, device) -> persistent uint8 scratch
         # called as hook(layer_index) right after the kernels producing that bucket's gradients are enqueued
         # (layer_index = num_layers for out_proj, L-1..0 for the layers, -1 for in_proj + latents)
         self.grad_ready_hook: Optional[Callable[[int], None]] = None
@@ -123,9 +129,15 @@ class PerceiverProjector(nn.Module):
         params = self._ordered_params()
         cc = self._compute
         if cc is None or cc["device"] != device or cc["ids"] != [id(p) for p in params]:
-            is_mat = [p.dim() == 2 for p in params]
-            bufs = [torch.empty(p.shape, device=device, dtype=torch.bfloat16 if m else torch.float32)
-                    for p, m in zip(params, is_mat)]
+            if self._flat_weights is not None:      # caller-owned flat storage (latents: bf16 copy next to it)
+                if self._flat_weights[0].device != device:
+                    raise RuntimeError("flat compute-copy storage lives on another device")
+                bufs = self._views_into(*self._flat_weights)
+                bufs[0] = torch.empty(params[0].shape, device=device, dtype=torch.bfloat16)
+            else:
+                is_mat = [p.dim() == 2 for p in params]
+                bufs = [torch.empty(p.shape, device=device, dtype=torch.bfloat16 if m else torch.float32)
+                        for p, m in zip(params, is_mat)]
             cc = {"device": device, "ids": [id(p) for p in params], "bufs": bufs, "versions": [-1] * len(params),
                   "ptrs": [None] * len(params), "structs": None}
             self._compute = cc
@@ -159,29 +171,66 @@ class PerceiverProjector(nn.Module):
             cc["structs"] = (w, arr)
         return cc
 
-    def grad_offsets(self) -> List[int]:
-        """Element offset of every parameter (in `_ordered_params` order) inside the flat gradient buffer; each
-        tensor is padded to a multiple of 64 elements so that every view is 256-byte aligned."""
-        offs, off = [], 0
+    def flat_layout(self) -> dict:
+        """Two-region flat layout shared by the gradient buffer, the compute copies and the sharded optimizer:
+        region "mat" = the Linear / in_proj weight matrices (what the wgrad GEMMs produce; bf16 on the wire), region
+        "vec" = biases, LayerNorm affine and the latents (f32 everywhere).  Every tensor starts at a multiple of 64
+        elements.  Returns {"kinds": [...], "offsets": [...], "mat": total, "vec": total} in `_ordered_params` order."""
+        kinds, offs, tot = [], [], {"mat": 0, "vec": 0}
         for p in self._ordered_params():
-            offs.append(off)
-            off += (p.numel() + 63) // 64 * 64
-        return offs + [off]
+            kind = "mat" if (p.dim() == 2 and p is not self.latents) else "vec"
+            kinds.append(kind)
+            offs.append(tot[kind])
+            tot[kind] += (p.numel() + 63) // 64 * 64
+        return {"kinds": kinds, "offsets": offs, "mat": tot["mat"], "vec": tot["vec"]}
+
+    def _views_into(self, mat: torch.Tensor, vec: torch.Tensor) -> List[torch.Tensor]:
+        lay = self.flat_layout()
+        out = []
+        for p, kind, off in zip(self._ordered_params(), lay["kinds"], lay["offsets"]):
+            src = mat if kind == "mat" else vec
+            out.append(src[off:off + p.numel()].view(p.shape))
+        return out
 
     def _grad_views(self, device: torch.device, fresh: bool = False) -> List[torch.Tensor]:
-        """Views, in `_ordered_params` order, into the flat f32 gradient buffer.  The buffer persists across steps
-        (`grad_flat`); `fresh=True` returns views into a new temporary buffer instead (used when some `p.grad` is
-        set but does not alias the persistent buffer, so that autograd accumulates the ordinary way)."""
-        params = self._ordered_params()
-        offs = self.grad_offsets()
+        """Views, in `_ordered_params` order, into the flat f32 gradient buffer ([mat region | vec region]).  The
+        buffer persists across steps (`grad_flat`); `fresh=True` returns views into a new temporary buffer instead
+        (used when some `p.grad` is set but does not alias the persistent buffer, so that autograd accumulates the
+        ordinary way)."""
+        lay = self.flat_layout()
+        total = lay["mat"] + lay["vec"]
         if not fresh and self._grad_flat is not None and self._grad_flat.device == device \
-                and self._grad_flat.numel() == offs[-1]:
+                and self._grad_flat.numel() == total:
             return self._grad_view_list
-        flat = torch.empty(offs[-1], device=device, dtype=torch.float32)
-        views = [flat[o:o + p.numel()].view(p.shape) for p, o in zip(params, offs)]
+        flat = torch.empty(total, device=device, dtype=torch.float32)
+        views = self._views_into(flat[:lay["mat"]], flat[lay["mat"]:])
         if not fresh:
             self._grad_flat, self._grad_view_list = flat, views
         return views
+
+    def use_flat_storage(self, weights_mat: torch.Tensor, weights_vec: torch.Tensor,
+                         grads_mat: Optional[torch.Tensor] = None, grads_vec: Optional[torch.Tensor] = None) -> None:
+        """Place the compute copies (bf16 matrices / f32 vectors) and, optionally, the gradients in caller-owned flat
+        buffers laid out as `flat_layout()` -- e.g. NVLink-symmetric memory owned by optim.ShardedAdamW, which then
+        updates the compute copies itself and all-gathers them between ranks.  With gradient buffers (grads_mat bf16
+        or f32, grads_vec f32) the backward writes there and hands NO gradient tensors to autograd (`p.grad` stays
+        None): the owner of the buffers consumes them."""
+        lay = self.flat_layout()
+        assert weights_mat.dtype == torch.bfloat16 and weights_vec.dtype == torch.float32
+        assert weights_mat.numel() >= lay["mat"] and weights_vec.numel() >= lay["vec"]
+        self._flat_weights = (weights_mat, weights_vec)
+        self._compute = None            # rebuilt on the next forward as views into the flat buffers
+        if grads_mat is not None:
+            assert grads_mat.dtype in (torch.bfloat16, torch.float32) and grads_vec.dtype == torch.float32
+            assert grads_mat.numel() >= lay["mat"] and grads_vec.numel() >= lay["vec"]
+            self._flat_grads = (grads_mat, grads_vec, self._views_into(grads_mat, grads_vec))
+        else:
+            self._flat_grads = None
+        self._flat_grads_fresh = True
+
+    def mark_grads_consumed(self) -> None:
+        """Owner of the flat gradient storage: the next backward overwrites it instead of accumulating."""
+        self._flat_grads_fresh = True
 
     @property
     def grad_flat(self) -> Optional[torch.Tensor]:
@@ -190,16 +239,16 @@ class PerceiverProjector(nn.Module):
 
     def _scratch(self, kind: str, nbytes: int, device: torch.device) -> torch.Tensor:
         """Persistent 1024-byte-aligned scratch (`saved` activations / workspace), reused while the size matches."""
-        buf = self._buffers.get(kind)
+        buf = self._scratch_bufs.get(kind)
         if buf is None or buf.numel() < nbytes + 1024 or buf.device != device:
             buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
-            self._buffers[kind] = buf
+            self._scratch_bufs[kind] = buf
         return buf
 
     def _lease_saved(self, nbytes: int, device: torch.device) -> "_Lease":
         """A `saved`-activations buffer from the module's pool (stable addresses across steps: the TMA descriptors
         cached by the library keep hitting); it goes back to the pool when the autograd graph that holds it dies."""
-        pool = self._buffers.setdefault("saved_pool", [])
+        pool = self._scratch_bufs.setdefault("saved_pool", [])
         for i, buf in enumerate(pool):
             if buf.numel() >= nbytes + 1024 and buf.device == device:
                 return _Lease(pool, pool.pop(i))
@@ -237,6 +286,8 @@ class PerceiverProjector(nn.Module):
             raise ValueError(f"expected tokens [B, T, {self.in_dim}], got {tuple(tokens.shape)}")
         if not tokens.is_cuda:
             raise RuntimeError("PerceiverProjector runs on sm_100a only: tokens must be a CUDA tensor (no CPU fallback)")
+        if self.before_forward is not None:
+            self.before_forward()
         return _PerceiverFunction.apply(self, tokens, *self._ordered_params())
 
 
@@ -295,13 +346,23 @@ class _PerceiverFunction(torch.autograd.Function):
         #  (b) every p.grad IS the matching view (gradient accumulation, zero_grad(set_to_none=False)): the kernels
         #      ACCUMULATE into the flat buffer in place and autograd gets no gradient tensors (nothing to add);
         #  (c) anything else (a foreign p.grad): a temporary buffer, ordinary autograd accumulation.
-        views = module._grad_views(dev)
-        has_grad = [p.grad is not None for p in params]
-        aliased = all(h and p.grad.data_ptr() == v.data_ptr() and p.grad.dtype == torch.float32
-                      for h, p, v in zip(has_grad, params, views))
-        in_place = aliased and any(has_grad)
-        if any(has_grad) and not in_place:
-            views = module._grad_views(dev, fresh=True)
+        #  (d) flat gradient storage owned by an optimizer (use_flat_storage): written / accumulated there, matrices
+        #      possibly in bf16; autograd gets no gradient tensors and `p.grad` stays None.
+        owned = module._flat_grads is not None
+        if owned:
+            views = module._flat_grads[2]
+            in_place = True
+            accumulate = 0 if module._flat_grads_fresh else 1
+            module._flat_grads_fresh = False
+        else:
+            views = module._grad_views(dev)
+            has_grad = [p.grad is not None for p in params]
+            aliased = all(h and p.grad.data_ptr() == v.data_ptr() and p.grad.dtype == torch.float32
+                          for h, p, v in zip(has_grad, params, views))
+            in_place = aliased and any(has_grad)
+            if any(has_grad) and not in_place:
+                views = module._grad_views(dev, fresh=True)
+            accumulate = 1 if in_place else 0
         n = len(_LAYER_PARAM_ORDER)
         gr = PerceiverGrads()
         gr.latents, gr.in_proj_w, gr.in_proj_b = views[0].data_ptr(), views[1].data_ptr(), views[2].data_ptr()
@@ -311,7 +372,8 @@ class _PerceiverFunction(torch.autograd.Function):
                 setattr(arr[l], field, views[3 + l * n + j].data_ptr())
         gr.layers = arr
         gr.out_proj_w, gr.out_proj_b = views[-2].data_ptr(), views[-1].data_ptr()
-        gr.accumulate = 1 if in_place else 0
+        gr.accumulate = accumulate
+        gr.weight_grad_bf16 = 1 if (owned and module._flat_grads[0].dtype == torch.bfloat16) else 0
         need_tok = ctx.needs_input_grad[1]
         grad_tok = torch.empty(cfg.B * cfg.T, cfg.in_dim, dtype=torch.float32, device=dev) if need_tok else None
         hook = module.grad_ready_hook
