@@ -66,8 +66,12 @@ def _worker(rank, world, port, q):
         opt.sync_parameters()
         worst = 0.0
         for name, p in m.named_parameters():
-            r, p0 = ref_state[name].detach(), state[name].cuda()
-            worst = max(worst, float((p.detach() - r).norm() / (r - p0).norm().clamp_min(1e-12)))
+            r, p0, got = ref_state[name].detach(), state[name].cuda(), p.detach()
+            if name.endswith("in_proj_bias"):   # key-bias gradient is identically zero: Adam steps on rounding noise
+                E = r.numel() // 3
+                keep = torch.cat([torch.arange(0, E), torch.arange(2 * E, 3 * E)]).cuda()
+                r, p0, got = r[keep], p0[keep], got[keep]
+            worst = max(worst, float((got - r).norm() / (r - p0).norm().clamp_min(1e-12)))
         # raw reduce numerics: bf16 slices summed in fp32
         n = opt.slice["mat"]
         gen = torch.Generator(device="cuda").manual_seed(7 + rank)

@@ -175,9 +175,15 @@ def test_sharded_adamw_single_gpu_training_steps(accumulate):
         opt.step()
     opt.sync_parameters()
     for name, p in m.named_parameters():
-        r, p0 = ref_state[name].detach(), state[name]
+        r, p0, got = ref_state[name].detach(), state[name], p.detach().cpu()
+        if name.endswith("in_proj_bias"):
+            # the gradient of the KEY bias is identically zero (softmax is invariant to a shift common to all keys); what
+            # is left is rounding noise, which Adam normalises to +-lr steps of arbitrary sign: not comparable
+            E = r.numel() // 3
+            keep = torch.cat([torch.arange(0, E), torch.arange(2 * E, 3 * E)])
+            r, p0, got = r[keep], p0[keep], got[keep]
         moved = (r - p0).norm()
-        err = (p.detach().cpu() - r).norm()
+        err = (got - r).norm()
         assert err <= 0.08 * moved + 1e-7, f"{name}: update error {err:.3e} vs update size {moved:.3e}"
     # the next forward reads the updated compute copies: same output as a fresh module loaded from the synced parameters
     x = torch.randn(2, 64, shape.in_dim, generator=g).cuda()
