@@ -151,6 +151,17 @@ int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32_t seq_len,
  *   emu_pairs       : 0..6 of every 8 exponential pairs evaluated on the FMA pipe instead of the MUFU (default 4;
  *                     the split-KV kernels are instantiated for 0..4) */
 int vq_attention_tune(int32_t q_tiles_per_cta, int32_t emu_pairs);
+/* The same op for callers that can GUARANTEE |q . k| <= score_bound <= 64 for every (query, key) pair of the buffer (q
+ * already carries the log2(e)/8 factor) -- the aggregator's frame / global blocks, whose q and k rows are per-head
+ * LayerNorm-ed so that the bound follows from the frozen q_norm / k_norm weights.  P = 2^s needs no row maximum, no
+ * range check and no rescale then, and every query row is served by two threads (csrc/attention.cu, "bounded"
+ * variant).  score_bound <= 0 or > 64 falls back to vq_attention_fwd.  Scores outside the promised bound give
+ * undefined probabilities (overflow), so the bound must be a proof, not an estimate. */
+int vq_attention_fwd_bounded(const void* qkv, void* out, int32_t n_seq, int32_t seq_len, int32_t heads,
+                             float score_bound, vq_stream_t stream);
+/* enable: 0 routes vq_attention_fwd_bounded to the checked kernel (A/B runs); emu_pairs as in vq_attention_tune (default 2);
+ * negative = keep */
+int vq_attention_tune_bounded(int32_t enable, int32_t emu_pairs);
 
 /* ------------------------------------------------------------------------------------------------
  * HBM-bound row kernels (csrc/rowops.cu)
@@ -281,6 +292,9 @@ typedef struct vq_block_weights {
   const void* fc2_w; /* bf16 [D, hidden] */
   const float* fc2_b;
   const float* ls2;
+  /* upper bound of |q . k| * log2(e)/8 over all token pairs, proven from q_norm / k_norm (host side:
+   * (8 max|w_q| + |b_q|_2)(8 max|w_k| + |b_k|_2) * log2(e)/8, rotation by RoPE preserves norms); 0 = unknown */
+  float qk_score_bound;
 } vq_block_weights;
 
 typedef struct vq_aggregator_weights {

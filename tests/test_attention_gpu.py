@@ -101,3 +101,52 @@ def test_attention_sequences_are_independent():
     torch.cuda.synchronize()
     assert torch.equal(a[:L], b[:L]) and torch.equal(a[2 * L:], b[2 * L:])
     assert not torch.equal(a[L:2 * L], b[L:2 * L])
+
+
+@pytest.mark.parametrize("emu", [0, 3, 6])
+@pytest.mark.parametrize("n_seq,L,heads", [(1, 128, 1), (2, 64, 2), (2, 65, 2), (3, 50, 1), (2, 129, 1), (2, 200, 2),
+                                           (2, 1374, 2), (1, 1, 1), (1, 257, 2), (1, 2 * 1374, 4), (1, 191, 1), (1, 193, 1)])
+def test_attention_bounded_variant(n_seq, L, heads, emu):
+    """vq_attention_fwd_bounded: scores proven <= 64 in magnitude (here: unit-norm-scaled q, k as after the per-head
+    LayerNorm of the aggregator blocks) -> no range check, two threads per query row; ragged tails in either key half."""
+    from vggt_qwen3_b200 import ops
+
+    ops.attention_tune_bounded(1, emu)
+    g = torch.Generator(device="cuda").manual_seed(5 + L)
+    HD = heads * 64
+    qkv = torch.randn(n_seq * L, 3 * HD, device="cuda", generator=g)
+    # rows of q and k normalised per head to norm 8 (what LayerNorm(64) produces), q additionally scaled by log2(e)/8:
+    # |s| <= 8 * 8 * 0.18 = 11.6
+    for blk, scale in ((0, math.log2(math.e) / 8.0), (1, 1.0)):
+        v = qkv[:, blk * HD:(blk + 1) * HD].view(-1, heads, 64)
+        v.copy_(v / v.norm(dim=-1, keepdim=True) * 8.0 * scale)
+    qkv = qkv.bfloat16()
+    out = ops.attention_fwd_bounded(qkv, n_seq, L, heads, 11.6 * 1.02)
+    torch.cuda.synchronize()
+    _check(out, _reference(qkv, n_seq, L, heads))
+    # the same call with the variant switched off (or without a bound) is the checked kernel: same tolerance
+    ops.attention_tune_bounded(0, -1)
+    _check(ops.attention_fwd_bounded(qkv, n_seq, L, heads, 11.6), _reference(qkv, n_seq, L, heads))
+    ops.attention_tune_bounded(1, 3)
+    _check(ops.attention_fwd_bounded(qkv, n_seq, L, heads, 0.0), _reference(qkv, n_seq, L, heads))
+
+
+def test_attention_bounded_at_the_bound():
+    """Scores that actually reach +-60 (inside the promised 64): P = 2^s spans 2^-60 .. 2^60 without a reference."""
+    from vggt_qwen3_b200 import ops
+
+    ops.attention_tune_bounded(1, 3)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n_seq, L, heads = 1, 700, 1
+    q = torch.randn(L, 64, device="cuda", generator=g)
+    k = torch.randn(L, 64, device="cuda", generator=g)
+    q = q / q.norm(dim=-1, keepdim=True) * 7.7
+    k = k / k.norm(dim=-1, keepdim=True) * 7.7
+    k[::50] = q[::50] / 7.7 * 7.7          # aligned pairs: s = 59.3
+    v = torch.randn(L, 64, device="cuda", generator=g)
+    qkv = torch.cat([q, k, v], dim=1).bfloat16()
+    s_max = (qkv[:, :64].float() @ qkv[:, 64:128].float().t()).abs().max().item()
+    assert 55.0 < s_max <= 64.0
+    out = ops.attention_fwd_bounded(qkv, n_seq, L, heads, 64.0)
+    torch.cuda.synchronize()
+    _check(out, _reference(qkv, n_seq, L, heads))

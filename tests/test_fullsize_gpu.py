@@ -70,6 +70,26 @@ def test_attention_long_sequence_auto_dispatch(n_seq, L, heads, kind):
         _check_rows(out, _attention_reference(qkv, n_seq, L, heads))
 
 
+@pytest.mark.parametrize("n_seq,L,heads", [(2, 8 * 1374, 2), (1, 32 * 1374, 1)])
+def test_attention_long_sequence_bounded_variant(n_seq, L, heads):
+    """The kernel the aggregator's frame / global blocks run (scores bounded through the QK LayerNorm) at the 8- and
+    32-frame global sequence lengths."""
+    from vggt_qwen3_b200 import ops
+
+    ops.attention_tune_bounded(1, 3)
+    with fp32_oracle_on_cuda():
+        g = torch.Generator(device="cuda").manual_seed(L)
+        HD = heads * 64
+        qkv = torch.randn(n_seq * L, 3 * HD, device="cuda", generator=g)
+        for blk, scale in ((0, math.log2(math.e) / 8.0), (1, 1.0)):
+            v = qkv[:, blk * HD:(blk + 1) * HD].view(-1, heads, 64)
+            v.copy_(v / v.norm(dim=-1, keepdim=True) * 8.0 * scale * 1.5)     # |s| <= 26
+        qkv = qkv.bfloat16()
+        out = ops.attention_fwd_bounded(qkv, n_seq, L, heads, 27.0)
+        torch.cuda.synchronize()
+        _check_rows(out, _attention_reference(qkv, n_seq, L, heads))
+
+
 # ------------------------------------------------------------------------------------------------ aggregator
 def _state_to(state, device):
     return {k: v.to(device) for k, v in state.items()}

@@ -184,7 +184,7 @@ def test_sharded_adamw_single_gpu_training_steps(accumulate):
             r, p0, got = r[keep], p0[keep], got[keep]
         moved = (r - p0).norm()
         err = (got - r).norm()
-        assert err <= 0.08 * moved + 1e-7, f"{name}: update error {err:.3e} vs update size {moved:.3e}"
+        assert err <= 0.12 * moved + 1e-7, f"{name}: update error {err:.3e} vs update size {moved:.3e}"
     # the next forward reads the updated compute copies: same output as a fresh module loaded from the synced parameters
     x = torch.randn(2, 64, shape.in_dim, generator=g).cuda()
     fresh = PerceiverProjector(PerceiverConfig(256, 64, 2, 2, 512, 0.0), in_dim=128, out_dim=192).cuda().eval()

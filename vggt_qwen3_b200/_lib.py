@@ -61,7 +61,8 @@ class BlockWeights(C.Structure):
 
     _fields_ = [(n, C.c_void_p) for n in (
         "norm1_w", "norm1_b", "qkv_w", "qkv_b", "q_norm_w", "q_norm_b", "k_norm_w", "k_norm_b",
-        "proj_w", "proj_b", "ls1", "norm2_w", "norm2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")]
+        "proj_w", "proj_b", "ls1", "norm2_w", "norm2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")] + [
+        ("qk_score_bound", C.c_float)]
 
 
 class AggregatorWeights(C.Structure):
@@ -155,6 +156,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.vq_attention_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.vq_attention_tune.restype = C.c_int
     lib.vq_attention_tune.argtypes = [C.c_int32, C.c_int32]
+    lib.vq_attention_fwd_bounded.restype = C.c_int
+    lib.vq_attention_fwd_bounded.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+    lib.vq_attention_tune_bounded.restype = C.c_int
+    lib.vq_attention_tune_bounded.argtypes = [C.c_int32, C.c_int32]
     lib.vq_preprocess_workspace_bytes.restype = C.c_size_t
     lib.vq_preprocess_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.vq_aggregator_workspace_bytes.restype = C.c_size_t

@@ -152,6 +152,7 @@ class Aggregator(nn.Module):
             if hasattr(b.attn, "q_norm"):
                 w.q_norm_w, w.q_norm_b = vec(b.attn.q_norm.weight), vec(b.attn.q_norm.bias)
                 w.k_norm_w, w.k_norm_b = vec(b.attn.k_norm.weight), vec(b.attn.k_norm.bias)
+                w.qk_score_bound = _qk_score_bound(b.attn.q_norm, b.attn.k_norm)
             w.proj_w, w.proj_b = mat(b.attn.proj.weight), vec(b.attn.proj.bias)
             w.ls1 = vec(b.ls1.gamma)
             w.norm2_w, w.norm2_b = vec(b.norm2.weight), vec(b.norm2.bias)
@@ -263,6 +264,18 @@ class Aggregator(nn.Module):
             return outs, self.patch_start_idx
         last = self.encode_tokens(images, None)
         return [last.view(B, S, -1, last.shape[-1])], self.patch_start_idx
+
+
+def _qk_score_bound(q_norm: nn.LayerNorm, k_norm: nn.LayerNorm) -> float:
+    """Proven upper bound of |q . k| * log2(e)/sqrt(64) for per-head LayerNorm-ed q and k: a normalised 64-vector has
+    norm <= 8, so |LN(x)| <= 8 max|w| + |b|_2; RoPE is a rotation and keeps norms.  The attention kernel uses it to
+    skip the softmax's range check (vq_attention_fwd_bounded); a margin of 2 % covers the bf16 rounding of q and k."""
+    def norm_bound(ln: nn.LayerNorm) -> float:
+        w = ln.weight.detach().float()
+        b = ln.bias.detach().float() if ln.bias is not None else torch.zeros_like(w)
+        return float(math.sqrt(w.numel()) * w.abs().max() + b.norm())
+
+    return 1.02 * norm_bound(q_norm) * norm_bound(k_norm) * math.log2(math.e) / 8.0
 
 
 def _rope_tables(max_pos: int, head_dim: int, freq: float) -> Tuple[torch.Tensor, torch.Tensor]:

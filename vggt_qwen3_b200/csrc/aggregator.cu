@@ -94,7 +94,7 @@ int run_block(const vq_aggregator_cfg* c, const vq_block_weights& bw, const vq_a
     rc = vq_gemm(&g, stream);
     if (rc) return rc;
   }
-  rc = vq_attention_fwd(ws.qkv, ws.att, n_seq, seq_len, c->heads, stream);
+  rc = vq_attention_fwd_bounded(ws.qkv, ws.att, n_seq, seq_len, c->heads, bw.q_norm_w ? bw.qk_score_bound : 0.f, stream);
   if (rc) return rc;
   // x += ls1 * (att Wp^T + b)
   {

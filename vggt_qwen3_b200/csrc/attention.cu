@@ -836,6 +836,247 @@ attention_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   }
 }
 
+
+// =====================================================================================================================
+// "Bounded" variant: the wide layout (one stream per 128-row query tile, S / O / P columns in TMEM, S(j+1) issued as
+// soon as S(j) is in registers) for callers that GUARANTEE |score| <= kFastBound -- the aggregator blocks, whose q and
+// k rows are per-head LayerNorm-ed: |q . k| * log2(e)/8 <= (8 max|w_q| + |b_q|)(8 max|w_k| + |b_k|) * 0.18, a bound the
+// host computes from the frozen weights (vq_block_weights.qk_score_bound).  With the bound known up front there is
+//  * no range-check / row-maximum pass and no rescale logic: P = 2^s straight away (3 dispatch slots per score on the
+//    MUFU path instead of 4-5), and
+//  * nothing two threads of a row have to agree on per step, so every query row is served by TWO threads, each owning
+//    64 of the step's 128 keys: 8 softmax warps per tile (16 per SM with two CTAs) instead of 4 (8) -- twice the
+//    warps to hide the TMEM round trips and barrier hand-offs behind; the partial row sums meet once, at the end.
+// Warps: 0..7 softmax (TMEM lane quarter = warp % 4, key half = warp / 4), 8 TMA producer, 9 MMA issuer, 10-11 idle.
+// =====================================================================================================================
+struct AttnBoundedCfg {
+  static constexpr int kSoftmaxWarps = 8;
+  static constexpr int kTmaWarp = 8;
+  static constexpr int kMmaWarp = 9;
+  static constexpr int kThreads = 12 * 32;
+  static constexpr int kStages = 3;
+  static constexpr int kTmemCols = 256;
+  // setmaxnreg moves registers inside the CTA's launch-time allocation: 384 x 80 = 256 x 104 + 128 x 32
+  static constexpr int kRegsSoftmax = 104;
+  static constexpr int kRegsLow = 32;
+  static constexpr int kNeeded = kTileBytes + 2 * kStages * kTileBytes + 256;
+  static constexpr int kSmemBytes = 115712;   // (228 KB - 2 KB) / 2: two CTAs per SM
+  static_assert(kNeeded <= kSmemBytes, "smem carve-up");
+};
+
+template <int EMU>
+__global__ void __launch_bounds__(AttnBoundedCfg::kThreads, 2)
+attention_fwd_bounded_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs g) {
+  using Cfg = AttnBoundedCfg;
+  constexpr int kKVStages = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (smem_base - smem_u32(smem_raw) + Cfg::kNeeded > Cfg::kSmemBytes) __trap();
+  const uint32_t smem_q = smem_base;
+  const uint32_t smem_k = smem_base + kTileBytes;
+  const uint32_t smem_v = smem_k + kKVStages * kTileBytes;
+  const uint32_t bar_base = smem_v + kKVStages * kTileBytes;
+  const uint32_t bar_qfull = bar_base;
+  const uint32_t bar_kfull = bar_base + 8;
+  const uint32_t bar_vfull = bar_kfull + 8 * kKVStages;
+  const uint32_t bar_kvempty = bar_vfull + 8 * kKVStages;
+  const uint32_t bar_sfull = bar_kvempty + 8 * kKVStages;
+  const uint32_t bar_sfree = bar_sfull + 8;
+  const uint32_t bar_pfull = bar_sfree + 8;
+  const uint32_t bar_pvdone = bar_pfull + 8;
+  const uint32_t tmem_slot = bar_pvdone + 8;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  float* l_buf = reinterpret_cast<float*>(smem_gen);   // [2 halves][128 rows] over the Q tile, dead by then
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;   // q-block fastest: K / V stay in L2
+  const int L = g.seq_len;
+  const int HD = g.heads * kHeadDim;
+  const int seq_row0 = seq * L;
+  const int q_row0 = qb * kTileQ;
+  const int n_kv = g.n_kv_tiles;
+
+  pdl_launch_dependents();
+  if (warp == Cfg::kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(bar_qfull, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(bar_kfull + 8 * s, 1);
+      mbar_init(bar_vfull + 8 * s, 1);
+      mbar_init(bar_kvempty + 8 * s, 1);
+    }
+    mbar_init(bar_sfull, 1);
+    mbar_init(bar_sfree, Cfg::kSoftmaxWarps);
+    mbar_init(bar_pfull, Cfg::kSoftmaxWarps);
+    mbar_init(bar_pvdone, 1);
+    fence_barrier_init();
+  }
+  if (warp == Cfg::kMmaWarp) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // qkv comes from the previous kernel
+
+  if (warp >= Cfg::kTmaWarp) {
+    setmaxnreg_dec<Cfg::kRegsLow>();
+    if (warp == Cfg::kTmaWarp) {
+      if (lane == 0) {
+        // ===================== TMA producer =====================
+        mbar_arrive_expect_tx(bar_qfull, kTileBytes);
+        tma_load_2d(smem_q, &tmQKV, bar_qfull, head * kHeadDim, seq_row0 + q_row0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < n_kv; ++j) {
+          mbar_wait(bar_kvempty + 8 * stage, phase ^ 1);
+          const int row = seq_row0 + j * kTileKV;
+          mbar_arrive_expect_tx(bar_kfull + 8 * stage, kTileBytes);
+          tma_load_2d(smem_k + stage * kTileBytes, &tmQKV, bar_kfull + 8 * stage, HD + head * kHeadDim, row);
+          mbar_arrive_expect_tx(bar_vfull + 8 * stage, kTileBytes);
+          tma_load_2d(smem_v + stage * kTileBytes, &tmQKV, bar_vfull + 8 * stage, 2 * HD + head * kHeadDim, row);
+          if (++stage == kKVStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == Cfg::kMmaWarp) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(kTileQ, kHeadDim, 0, 1);  // V is MN-major (d contiguous)
+      const uint64_t desc_q = make_smem_desc(smem_q, 16, 1024);
+      const uint64_t desc_k = make_smem_desc(smem_k, 16, 1024);
+      const uint64_t desc_v = make_smem_desc(smem_v, 8192, 1024);
+      const uint32_t tS = tmem_base, tO = tS + 128, tP = tS + 192;
+      auto issue_s = [&](int stage) {
+        if (elect_one()) {
+          const uint64_t b0 = desc_k + (uint64_t)(stage * (kTileBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            umma_ss(tS, desc_q + (uint64_t)(k * 2), b0 + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+          umma_commit(bar_sfull);
+        }
+        __syncwarp();
+      };
+      mbar_wait(bar_qfull, 0);
+      mbar_wait(bar_kfull, 0);
+      tc_fence_after();
+      issue_s(0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        const int nstage = (stage + 1 == kKVStages) ? 0 : stage + 1;
+        const uint32_t nphase = (stage + 1 == kKVStages) ? (phase ^ 1) : phase;
+        if (j + 1 < n_kv) {
+          mbar_wait_fast(bar_kfull + 8 * nstage, nphase);
+          mbar_wait_fast(bar_sfree, j & 1);     // S(j) is in registers: its columns may be overwritten
+          tc_fence_after();
+          issue_s(nstage);
+        }
+        mbar_wait_fast(bar_vfull + 8 * stage, phase);
+        mbar_wait_fast(bar_pfull, j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t b0 = desc_v + (uint64_t)(stage * (kTileBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < kTileKV / 16; ++k)
+            umma_ts(tO, tP + k * 8, b0 + (uint64_t)(k * 128), idesc_o, (j | k) ? 1u : 0u);
+          umma_commit(bar_pvdone);
+          umma_commit(bar_kvempty + 8 * stage);
+        }
+        __syncwarp();
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ===================== softmax warps: two threads per query row =====================
+    setmaxnreg_inc<Cfg::kRegsSoftmax>();
+    const int quarter = warp & 3;
+    const int half = warp >> 2;                 // keys [64 half, 64 half + 64) of every step
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + half * 64;
+    const uint32_t tO = tmem_base + lane_addr + 128;
+    const uint32_t tP = tmem_base + lane_addr + 192 + half * 32;
+    float l_run = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait_trap(bar_sfull, j & 1);
+      tc_fence_after();
+      float s[64];
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tS, r0);
+        tmem_ld32(tS + 32, r1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s[i] = __uint_as_float(r0[i]);
+          s[32 + i] = __uint_as_float(r1[i]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree);
+
+      uint32_t p[32];
+      const int n_valid = L - j * kTileKV - half * 64;   // keys of this half inside the sequence
+      if (n_valid >= 64) {
+        l_run += exp_row_fast<EMU, 64>(s, p);
+      } else {
+        // ragged last tile: masked keys get probability exactly 0 (ex2(-inf) on the MUFU; the emulation cannot)
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= n_valid) s[i] = -INFINITY;
+        l_run += exp_row<0, 0, 64>(s, 0.f, p);
+      }
+      if (j > 0) {
+        mbar_wait_trap(bar_pvdone, (j - 1) & 1);   // P(j-1) V has retired: the P columns are free
+        tc_fence_after();
+      }
+      tmem_st32(tP, p);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pfull);
+    }
+
+    // ---- the two halves of a row exchange their partial sums; each writes 32 of the 64 output columns
+    mbar_wait_trap(bar_pvdone, (n_kv - 1) & 1);    // every MMA has retired: O is final, the Q tile is dead
+    tc_fence_after();
+    l_buf[half * kTileQ + row] = l_run;
+    named_bar_sync(1, Cfg::kSoftmaxWarps * 32);
+    const float inv_l = 1.0f / (l_run + l_buf[(half ^ 1) * kTileQ + row]);
+    const int q_in_seq = q_row0 + row;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) + (long long)(seq_row0 + q_in_seq) * HD +
+                         head * kHeadDim + half * 32;
+    uint32_t o[32];
+    tmem_ld32(tO + half * 32, o);
+    tmem_wait_ld();
+    if (q_in_seq < L) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+        u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+        u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(dst + i) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == Cfg::kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 }  // namespace vq
 
 namespace vq {
@@ -855,6 +1096,54 @@ static int g_attn_dbg = env_int("VQ_ATTN_DBG", 0, 0, 63);  // timing experiments
 extern "C" int vq_attention_tune(int32_t q_tiles_per_cta, int32_t emu_pairs) {
   if (q_tiles_per_cta >= 0) vq::g_attn_qt = q_tiles_per_cta > 4 ? 4 : q_tiles_per_cta;
   if (emu_pairs >= 0) vq::g_attn_emu = emu_pairs > 6 ? 6 : emu_pairs;
+  return VQ_OK;
+}
+
+static int g_attn_bounded_emu = vq::env_int("VQ_ATTN_BOUNDED_EMU", 2, 0, 6);
+static int g_attn_bounded_on = vq::env_int("VQ_ATTN_BOUNDED", 1, 0, 1);
+
+extern "C" int vq_attention_fwd_bounded(const void* qkv, void* out, int32_t n_seq, int32_t seq_len, int32_t heads,
+                                        float score_bound, vq_stream_t stream_) {
+  using namespace vq;
+  // without a usable bound (or with the variant switched off for A/B runs) this is the checked kernel
+  if (!(score_bound > 0.f && score_bound <= kFastBound) || !g_attn_bounded_on)
+    return vq_attention_fwd(qkv, out, n_seq, seq_len, heads, stream_);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(qkv && out, "qkv/out must be non-null");
+  VQ_CHECK_ARG(n_seq > 0 && seq_len > 0 && heads > 0, "n_seq, seq_len, heads must be positive");
+  VQ_CHECK_ARG(n_seq <= 65535 && heads <= 65535, "grid limits");
+  VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(out) % 16) == 0, "out alignment");
+  const long long rows = (long long)n_seq * seq_len;
+  VQ_CHECK_ARG(rows + 512 < INT32_MAX, "too many rows");
+  const int HD = heads * kHeadDim;
+  const CUtensorMap* tm = get_tmap_2d_bf16(qkv, 3ull * HD, (uint64_t)rows, 3ull * HD, 64, 128);
+  if (!tm) return VQ_ERR_CUDA;
+  using Kern = void (*)(const CUtensorMap, const AttnArgs);
+  const int emu = g_attn_bounded_emu;
+  Kern kern = emu == 0 ? attention_fwd_bounded_kernel<0> : emu == 1 ? attention_fwd_bounded_kernel<1>
+            : emu == 2 ? attention_fwd_bounded_kernel<2> : emu == 3 ? attention_fwd_bounded_kernel<3>
+            : emu == 4 ? attention_fwd_bounded_kernel<4> : emu == 5 ? attention_fwd_bounded_kernel<5>
+                                                                   : attention_fwd_bounded_kernel<6>;
+  VQ_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), AttnBoundedCfg::kSmemBytes, true));
+  AttnArgs g;
+  g.out = out;
+  g.seq_len = seq_len;
+  g.heads = heads;
+  g.n_kv_tiles = (seq_len + kTileKV - 1) / kTileKV;
+  dim3 grid((seq_len + kTileQ - 1) / kTileQ, heads, n_seq);
+  {
+    const double flops = 4.0 * n_seq * heads * (double)seq_len * seq_len * kHeadDim;
+    const double bytes = 2.0 * (double)rows * HD * 4.0;
+    LaunchScope scope(kKindAttention, "attention_fwd_bounded", n_seq, seq_len, heads, flops, bytes, stream);
+    VQ_CHECK_CUDA(launch_pdl(kern, grid, dim3(AttnBoundedCfg::kThreads), (size_t)AttnBoundedCfg::kSmemBytes, stream, *tm, g));
+  }
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
+}
+
+extern "C" int vq_attention_tune_bounded(int32_t enable, int32_t emu_pairs) {
+  if (enable >= 0) g_attn_bounded_on = enable ? 1 : 0;
+  if (emu_pairs >= 0) g_attn_bounded_emu = emu_pairs > 6 ? 6 : emu_pairs;
   return VQ_OK;
 }
 
@@ -919,13 +1208,7 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
   const int smem_bytes = qt == 4 ? AttnWideCfg<1>::kSmemBytes : qt == 3 ? AttnWideCfg<2>::kSmemBytes : qt == 2 ? AttnCfg<2>::kSmemBytes : AttnCfg<1>::kSmemBytes;
   const int threads = qt == 4 ? AttnWideCfg<1>::kThreads : qt == 3 ? AttnWideCfg<2>::kThreads : qt == 2 ? AttnCfg<2>::kThreads : AttnCfg<1>::kThreads;
   const int q_tiles = (qt == 1 || qt == 4) ? 1 : 2;
-  static bool configured[5][7] = {};
-  if (!configured[qt][emu] || dbg) {
-    VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       cudaSharedmemCarveoutMaxShared));
-    configured[qt][emu] = true;
-  }
+  VQ_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_bytes, true));
   AttnArgs g;
   g.out = out;
   g.seq_len = seq_len;

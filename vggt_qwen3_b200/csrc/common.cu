@@ -98,14 +98,39 @@ bool pdl_enabled() {
   return on;
 }
 
+// per-device caches (a process may touch more than one GPU; function attributes and the SM count are per device)
+constexpr int kMaxDevices = 64;
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  static int n[kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 0;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
+}
+
+cudaError_t ensure_dynamic_smem(const void* func, int bytes, bool max_carveout) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> done;   // (device, function) -> bytes configured
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t key = (reinterpret_cast<uint64_t>(func) << 6) ^ (uint64_t)(dev & 63);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  if (max_carveout) {
+    e = cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+  }
+  done[key] = bytes;
+  return cudaSuccess;
 }
 
 // ------------------------------------------------------------------ launch accounting / profiling

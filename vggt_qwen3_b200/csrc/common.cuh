@@ -36,7 +36,11 @@ void set_error(const std::string& msg);
 const CUtensorMap* get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
                                     uint32_t box_inner, uint32_t box_outer);
 
-int num_sms();
+int num_sms();   // of the current device
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize (and optionally the max-shared carve-out) for `func` on the CURRENT device,
+// set once per (device, function); thread-safe.
+cudaError_t ensure_dynamic_smem(const void* func, int bytes, bool max_carveout = false);
 
 // Programmatic dependent launch (VQ_PDL=0 disables it): kernels of the hot chain (GEMM, attention, LayerNorm) are
 // launched with cudaLaunchAttributeProgrammaticStreamSerialization so that their prologue (barrier init, TMEM

@@ -657,11 +657,7 @@ template <int BLOCK_N, int MODE, bool OUT_F32, int CG>
 static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
   auto kern = gemm_kernel<BLOCK_N, MODE, OUT_F32, CG>;
-  static bool configured = false;
-  if (!configured) {
-    VQ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  VQ_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes));
   const int sms = num_sms();
   int grid;
   if (CG == 2) {

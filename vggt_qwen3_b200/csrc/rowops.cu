@@ -238,11 +238,7 @@ extern "C" int vq_im2col_patches(const float* images, void* out_bf16, int32_t fr
   VQ_CHECK_ARG(Kp >= 3 * patch * patch && Kp % 8 == 0, "Kp must be >= 3*patch^2 and a multiple of 8");
   const size_t smem = (size_t)3 * patch * gw * patch * sizeof(__nv_bfloat16);
   VQ_CHECK_ARG(smem <= 200 * 1024, "image too wide for the im2col strip");
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    VQ_CHECK_CUDA(cudaFuncSetAttribute(im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 48 * 1024) VQ_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(im2col_kernel), (int)smem));
   LaunchScope scope(kKindRow, "im2col", frames, H, W, 0, (double)frames * (3.0 * H * W * 4 + (double)gh * gw * Kp * 2), stream);
   im2col_kernel<<<frames * gh, 256, smem, stream>>>(images, reinterpret_cast<__nv_bfloat16*>(out_bf16), H, W, patch,
                                                     gh, gw, Kp);

@@ -117,6 +117,22 @@ def attention_fwd(qkv: torch.Tensor, n_seq: int, seq_len: int, heads: int,
     return out
 
 
+def attention_fwd_bounded(qkv: torch.Tensor, n_seq: int, seq_len: int, heads: int, score_bound: float,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`attention_fwd` for buffers whose scores are PROVEN to satisfy |q . k| <= score_bound <= 64 (see the header)."""
+    _req(qkv, torch.bfloat16, "qkv")
+    assert qkv.dim() == 2 and qkv.is_contiguous() and qkv.shape == (n_seq * seq_len, 3 * heads * 64)
+    if out is None:
+        out = torch.empty((n_seq * seq_len, heads * 64), device=qkv.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().vq_attention_fwd_bounded(qkv.data_ptr(), out.data_ptr(), n_seq, seq_len, heads,
+                                                   float(score_bound), _stream()), "vq_attention_fwd_bounded")
+    return out
+
+
+def attention_tune_bounded(enable: int = -1, emu_pairs: int = -1) -> None:
+    _lib.check(_lib.lib().vq_attention_tune_bounded(enable, emu_pairs), "vq_attention_tune_bounded")
+
+
 def attention_tune(q_tiles_per_cta: int = -1, emu_pairs: int = -1) -> None:
     """Force an attention kernel variant (tests / tuning); -1 keeps the current setting, q_tiles_per_cta=0 = auto."""
     _lib.check(_lib.lib().vq_attention_tune(q_tiles_per_cta, emu_pairs), "vq_attention_tune")
