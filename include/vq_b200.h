@@ -14,7 +14,7 @@
  *  - All pointers are CUDA device pointers owned by the caller (PyTorch); the library never allocates
  *    or frees caller memory.  Rows are 16-byte aligned.  Work is enqueued on `stream` and the call
  *    returns without synchronising.  One process per GPU; functions are re-entrant; the only global
- *    state is a cache of immutable TMA descriptors keyed by (pointer, shape, box).
+ *    state is a bounded (LRU, 2048 entries) cache of immutable TMA descriptors keyed by (pointer, shape, box).
  *  - "bf16" buffers hold IEEE bfloat16; "f32" buffers hold float.
  */
 #ifndef VQ_B200_H_

@@ -77,3 +77,78 @@ def test_flat_and_legacy_layouts(tmp_path):
     empty = tmp_path / "empty"
     empty.mkdir()
     assert ck.load_checkpoint_dir(_Wrapper(7), empty) is None
+
+
+def test_training_state_directory_round_trip(tmp_path):
+    """`step_N/` directories (src/train/train_sft.py:177-190,250-257): merged f32 weights in the layout the reference's
+    loader reads + per-rank optimizer shard + scheduler.bin + random_states_0.pkl; resuming restores all of them."""
+    import math
+    import random
+
+    from tests.test_dist_cpu import TorchKernels
+    from vggt_qwen3_b200.checkpoint_io import load_training_state, save_step
+    from vggt_qwen3_b200.optim import ShardedAdamW
+    from vggt_qwen3_b200.projector_perceiver import PerceiverConfig, PerceiverProjector
+
+    class Wrap(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.projector = PerceiverProjector(PerceiverConfig(64, 64, 2, 1, 128, 0.0), in_dim=32, out_dim=48)
+            self.geom_head = torch.nn.Sequential(torch.nn.Linear(37, 48), torch.nn.SiLU(), torch.nn.Linear(48, 48))
+
+    def train_two_steps(m, opt, sched):
+        for step in range(2):
+            g = torch.Generator().manual_seed(step)
+            for v in m.projector._flat_grads[2]:
+                v.copy_(torch.randn(v.shape, generator=g))
+            for p in m.geom_head.parameters():
+                p.grad = torch.randn(p.shape, generator=g)
+            opt.step()
+            sched.step()
+            opt.zero_grad()
+
+    def build():
+        m = Wrap()
+        opt = ShardedAdamW(m.projector, lr=1e-2, weight_decay=0.01, extra_params=m.geom_head.parameters(),
+                           kernels=TorchKernels())
+        sched = torch.optim.lr_scheduler.LambdaLR(_SchedShim(opt), lambda s: 1.0 / (1 + s))
+        return m, opt, sched
+
+    class _SchedShim(torch.optim.Optimizer):     # LR schedulers want a torch Optimizer; they only touch param_groups
+        def __init__(self, opt):
+            self.__dict__["_opt"] = opt
+            super().__init__(opt.param_groups[0]["params"], {"lr": opt.param_groups[0]["lr"]})
+            self.param_groups = opt.param_groups
+
+        def step(self, closure=None):
+            pass
+
+    m, opt, sched = build()
+    train_two_steps(m, opt, sched)
+    random.seed(7)
+    torch.manual_seed(11)
+    root = save_step(m, tmp_path, 1500, optimizer=opt, scheduler=sched)
+    assert root.name == "step_1500"
+    for name in ("pytorch_model_fp32/pytorch_model.bin.index.json", "scheduler.bin", "random_states_0.pkl",
+                 "optimizer_rank0.bin", "latest"):
+        assert (root / name).exists(), name
+    expect_rand, expect_torch = random.random(), torch.rand(3)
+    want = {k: v.clone() for k, v in m.state_dict().items()}
+    want_master = {k: v.clone() for k, v in opt.master.items()}
+    lr_after = opt.param_groups[0]["lr"]
+
+    m2, opt2, sched2 = build()        # fresh run, resumes
+    found = load_training_state(m2, root, optimizer=opt2, scheduler=sched2)
+    assert found == {"weights": True, "optimizer": True, "scheduler": True, "rng": True, "step": 1500}
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, want[k]), k
+    assert all(torch.equal(opt2.master[k], want_master[k]) for k in want_master) and opt2.step_count == 2
+    assert math.isclose(opt2.param_groups[0]["lr"], lr_after)
+    assert random.random() == expect_rand and torch.equal(torch.rand(3), expect_torch)
+    # and training continues identically
+    train_two_steps(m, opt, sched)
+    train_two_steps(m2, opt2, sched2)
+    opt.sync_parameters(); opt2.sync_parameters()
+    for (k, a), b in zip(m.state_dict().items(), m2.state_dict().values()):
+        assert torch.equal(a, b), k

@@ -105,3 +105,97 @@ def load_checkpoint_dir(model: torch.nn.Module, ckpt_dir) -> Optional[Tuple[List
         return None
     res = model.load_state_dict(_load_file(files[0]), strict=False)
     return list(res.missing_keys), list(res.unexpected_keys)
+
+
+# ------------------------------------------------------------------------------------------------
+# Training-state directories (resume): what the reference gets from `accelerator.save_state(dir)` every
+# `save_every_steps` steps and at the end (src/train/train_sft.py:177-190,250-257) -- `step_N/` directories holding
+# the model, the (per-rank, sharded) optimizer state, `scheduler.bin` and `random_states_{rank}.pkl`.  Same file names
+# for the pieces Accelerate names; the model goes straight to the merged `pytorch_model_fp32/` layout the reference's
+# inference loader reads (no `zero_to_fp32.py` pass needed: the masters are gathered at save time).
+# ------------------------------------------------------------------------------------------------
+SCHEDULER_NAME = "scheduler.bin"
+RNG_NAME = "random_states_{rank}.pkl"
+OPTIMIZER_NAME = "optimizer_rank{rank}.bin"
+
+
+def _rng_states() -> dict:
+    import random
+
+    import numpy as np
+
+    states = {"random_state": random.getstate(), "numpy_random_seed": np.random.get_state(),
+              "torch_manual_seed": torch.get_rng_state()}           # Accelerate's keys (accelerate/checkpointing.py)
+    if torch.cuda.is_available():
+        states["torch_cuda_manual_seed"] = torch.cuda.get_rng_state_all()
+    return states
+
+
+def _restore_rng(states: dict) -> None:
+    import random
+
+    import numpy as np
+
+    random.setstate(states["random_state"])
+    np.random.set_state(states["numpy_random_seed"])
+    torch.set_rng_state(states["torch_manual_seed"])
+    if torch.cuda.is_available() and "torch_cuda_manual_seed" in states:
+        torch.cuda.set_rng_state_all(states["torch_cuda_manual_seed"])
+
+
+def save_training_state(model: torch.nn.Module, ckpt_dir, optimizer=None, scheduler=None, step: Optional[int] = None,
+                        rank: int = 0, world: int = 1) -> Path:
+    """EVERY rank calls this (like the reference's `save_checkpoint`, train_sft.py:177-190): rank 0 writes the merged
+    f32 weights (`pytorch_model_fp32/`), `scheduler.bin` and `latest`; every rank writes its optimizer shard and RNG
+    state.  With `optim.ShardedAdamW` the f32 masters are gathered into the module first (`sync_parameters`, a
+    collective: hence every rank)."""
+    root = Path(ckpt_dir)
+    if optimizer is not None and hasattr(optimizer, "sync_parameters"):
+        optimizer.sync_parameters()
+    if rank == 0:
+        root.mkdir(parents=True, exist_ok=True)
+        save_trainable_checkpoint(model, root)
+        if scheduler is not None:
+            torch.save(scheduler.state_dict(), root / SCHEDULER_NAME)
+        if step is not None:
+            (root / "latest").write_text(f"step_{step}\n")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    root.mkdir(parents=True, exist_ok=True)
+    if optimizer is not None:
+        torch.save(optimizer.state_dict(), root / OPTIMIZER_NAME.format(rank=rank))
+    torch.save(_rng_states(), root / RNG_NAME.format(rank=rank))
+    return root
+
+
+def load_training_state(model: torch.nn.Module, ckpt_dir, optimizer=None, scheduler=None, rank: int = 0) -> dict:
+    """Resume from a directory written by `save_training_state`: weights (through the reference's resolution order),
+    this rank's optimizer shard, the scheduler and the RNG streams (so that the dropout masks of the resumed run are
+    the ones the uninterrupted run would have drawn).  Returns what was found."""
+    root = Path(ckpt_dir)
+    found = {"weights": load_checkpoint_dir(model, root) is not None, "optimizer": False, "scheduler": False,
+             "rng": False, "step": None}
+    opt_file = root / OPTIMIZER_NAME.format(rank=rank)
+    if optimizer is not None and opt_file.exists():
+        if hasattr(optimizer, "reload_masters"):
+            optimizer.reload_masters()       # the weights just loaded
+        optimizer.load_state_dict(torch.load(opt_file, map_location="cpu", weights_only=False))
+        found["optimizer"] = True
+    if scheduler is not None and (root / SCHEDULER_NAME).exists():
+        scheduler.load_state_dict(torch.load(root / SCHEDULER_NAME, map_location="cpu", weights_only=False))
+        found["scheduler"] = True
+    rng_file = root / RNG_NAME.format(rank=rank)
+    if rng_file.exists():
+        _restore_rng(torch.load(rng_file, map_location="cpu", weights_only=False))
+        found["rng"] = True
+    if (root / "latest").exists():
+        tag = (root / "latest").read_text().strip()
+        found["step"] = int(tag.split("_")[-1]) if tag.split("_")[-1].isdigit() else None
+    return found
+
+
+def save_step(model: torch.nn.Module, output_dir, step: int, **kw) -> Path:
+    """`<output_dir>/step_<N>/` like the reference's periodic save (train_sft.py:250-254)."""
+    return save_training_state(model, Path(output_dir) / f"step_{step}", step=step, **kw)

@@ -1116,8 +1116,9 @@ extern "C" int vq_attention_fwd_bounded(const void* qkv, void* out, int32_t n_se
   const long long rows = (long long)n_seq * seq_len;
   VQ_CHECK_ARG(rows + 512 < INT32_MAX, "too many rows");
   const int HD = heads * kHeadDim;
-  const CUtensorMap* tm = get_tmap_2d_bf16(qkv, 3ull * HD, (uint64_t)rows, 3ull * HD, 64, 128);
-  if (!tm) return VQ_ERR_CUDA;
+  CUtensorMap map;
+  if (!get_tmap_2d_bf16(qkv, 3ull * HD, (uint64_t)rows, 3ull * HD, 64, 128, &map)) return VQ_ERR_CUDA;
+  const CUtensorMap* tm = &map;
   using Kern = void (*)(const CUtensorMap, const AttnArgs);
   const int emu = g_attn_bounded_emu;
   Kern kern = emu == 0 ? attention_fwd_bounded_kernel<0> : emu == 1 ? attention_fwd_bounded_kernel<1>
@@ -1158,8 +1159,9 @@ extern "C" int vq_attention_fwd(const void* qkv, void* out, int32_t n_seq, int32
   const long long rows = (long long)n_seq * seq_len;
   VQ_CHECK_ARG(rows + 512 < INT32_MAX, "too many rows");
   const int HD = heads * kHeadDim;
-  const CUtensorMap* tm = get_tmap_2d_bf16(qkv, 3ull * HD, (uint64_t)rows, 3ull * HD, 64, 128);
-  if (!tm) return VQ_ERR_CUDA;
+  CUtensorMap map;
+  if (!get_tmap_2d_bf16(qkv, 3ull * HD, (uint64_t)rows, 3ull * HD, 64, 128, &map)) return VQ_ERR_CUDA;
+  const CUtensorMap* tm = &map;
 
   const int emu = g_attn_emu;
   const int emu4 = emu > 4 ? 4 : emu;   // the split-KV kernels are instantiated for 0..4

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <cstring>
+#include <list>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
@@ -54,40 +55,56 @@ struct TmapKeyHash {
   }
 };
 
-const CUtensorMap* get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                                    uint32_t box_inner, uint32_t box_outer) {
+// Bounded LRU cache: descriptors are keyed by every argument (base pointer included), so a caller that allocates fresh
+// buffers every step would otherwise grow the cache without limit.  Entries are copied out under the lock, so eviction
+// can never invalidate a descriptor a launch is about to use.
+constexpr size_t kTmapCacheCapacity = 2048;
+
+bool get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                      uint32_t box_outer, CUtensorMap* out) {
+  struct Entry { TmapKey key; CUtensorMap map; };
   static std::mutex mu;
-  static std::unordered_map<TmapKey, std::unique_ptr<CUtensorMap>, TmapKeyHash> cache;
+  static std::list<Entry> lru;   // front = most recently used
+  static std::unordered_map<TmapKey, std::list<Entry>::iterator, TmapKeyHash> index;
   TmapKey key{base, inner, outer, ld, box_inner, box_outer};
   std::lock_guard<std::mutex> lock(mu);
-  auto it = cache.find(key);
-  if (it != cache.end()) return it->second.get();
-
+  auto it = index.find(key);
+  if (it != index.end()) {
+    lru.splice(lru.begin(), lru, it->second);
+    *out = it->second->map;
+    return true;
+  }
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
-    return nullptr;
+    return false;
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * 2) & 15u) != 0 || box_inner != 64 ||
       box_outer == 0 || box_outer > 256 || inner == 0 || outer == 0) {
     set_error("tensor map: base/pitch must be 16-byte aligned, box = {64, 1..256}, extents > 0");
-    return nullptr;
+    return false;
   }
-  std::unique_ptr<CUtensorMap> tm(new CUtensorMap);
+  Entry e;
+  e.key = key;
   cuuint64_t gdim[2] = {inner, outer};
   cuuint64_t gstride[1] = {ld * 2};  // bytes, dims 1..rank-1
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm.get(), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+  CUresult r = enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
                    gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
-    return nullptr;
+    return false;
   }
-  const CUtensorMap* out = tm.get();
-  cache.emplace(key, std::move(tm));
-  return out;
+  lru.push_front(e);
+  index[key] = lru.begin();
+  if (lru.size() > kTmapCacheCapacity) {
+    index.erase(lru.back().key);
+    lru.pop_back();
+  }
+  *out = e.map;
+  return true;
 }
 
 bool pdl_enabled() {

@@ -31,10 +31,10 @@ void set_error(const std::string& msg);
 
 // 2-D bf16 tensor map with SWIZZLE_128B.  `inner`/`outer` are the tensor extents in elements,
 // `ld` the row pitch in elements, box = {box_inner (must be 64), box_outer}.
-// Returns nullptr (and sets the error string) on failure.  Descriptors are cached for the life of
-// the process, keyed by every argument; they are immutable.
-const CUtensorMap* get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                                    uint32_t box_inner, uint32_t box_outer);
+// Copies the descriptor into *out; returns false (and sets the error string) on failure.  Descriptors are cached in a
+// bounded LRU keyed by every argument; they are immutable.
+bool get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                      uint32_t box_outer, CUtensorMap* out);
 
 int num_sms();   // of the current device
 

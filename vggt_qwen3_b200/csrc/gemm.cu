@@ -773,12 +773,10 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
   const long long b_cols = d->b_cols > 0 ? d->b_cols : b_inner_need;
   VQ_CHECK_ARG(d->lda >= a_cols && d->ldb >= b_cols, "lda/ldb smaller than the row extent");
 
-  const CUtensorMap* tmA =
-      get_tmap_2d_bf16(d->A, a_cols, a_rows, d->lda, 64, d->a_major ? kBlockK : kBlockM);
-  if (!tmA) return VQ_ERR_CUDA;
-  const CUtensorMap* tmB =
-      get_tmap_2d_bf16(d->B, b_cols, b_rows, d->ldb, 64, d->b_major ? kBlockK : block_n / cg);
-  if (!tmB) return VQ_ERR_CUDA;
+  CUtensorMap mapA, mapB;
+  if (!get_tmap_2d_bf16(d->A, a_cols, a_rows, d->lda, 64, d->a_major ? kBlockK : kBlockM, &mapA)) return VQ_ERR_CUDA;
+  if (!get_tmap_2d_bf16(d->B, b_cols, b_rows, d->ldb, 64, d->b_major ? kBlockK : block_n / cg, &mapB)) return VQ_ERR_CUDA;
+  const CUtensorMap *tmA = &mapA, *tmB = &mapB;
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));
