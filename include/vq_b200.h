@@ -128,6 +128,22 @@ typedef struct vq_gemm_desc {
   /* Dropout on the epilogue value BEFORE gamma / add (unbatched LINEAR, GELU: after the activation; GELU_BWD: the
    * incoming gradient is masked with the forward's mask); element index = (row m, column n) with ld = N. */
   vq_dropout_desc dropout;
+
+  /* LayerNorm folded into the GEMMs around it (the aggregator's pre-norm blocks: no standalone LayerNorm launch).
+   * Consumer side (ln_stats != NULL; LINEAR / GELU / QKV_ROPE, unbatched, A K-major): A holds the RAW rows x (bf16),
+   * B the gamma-scaled weight W' = W diag(gamma_ln); with ln_stats[m] = (sum_k x, sum_k x^2) of row m (f32, over the
+   * K = ln_dim features), ln_colsum[n] = sum_k W'[n,k] and bias = W beta_ln + b the epilogue computes
+   *     LN(x) W^T + b = rstd_m (x W'^T - mean_m ln_colsum) + bias.
+   * Producer side (LINEAR, f32 output): stats_out[m] += (sum_n C[m,n], sum_n C[m,n]^2) over the columns this launch
+   * writes (atomics; the buffer must be zero when the launch starts), c_copy_bf16 receives a bf16 copy of C (same ldc),
+   * and stats_zero (2*M floats) is cleared after the launch's stream dependency has resolved -- the buffer the NEXT
+   * producer accumulates into, so two buffers ping-pong through a chain of blocks without memset launches. */
+  const float* ln_stats;
+  const float* ln_colsum;
+  float ln_eps;
+  float* stats_out;
+  float* stats_zero;
+  void* c_copy_bf16;
 } vq_gemm_desc;
 
 int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream);
@@ -183,6 +199,11 @@ int vq_init_special_tokens(float* x, const float* cls_token, const float* pos_em
 int vq_layernorm(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, const float* gamma,
                  const float* beta, int64_t rows, int32_t D, float eps, float* mean_out, float* rstd_out,
                  vq_stream_t stream);
+
+/* Entry of a LayerNorm-folded block chain: stats[m] = (sum, sum of squares) of row m of x (f32 [rows, D]), xb = bf16(x),
+ * stats_zero (optional, 2*rows floats) cleared: what the proj / fc2 epilogues maintain from then on. */
+int vq_row_stats_cast(const float* x, void* xb_bf16, float* stats, float* stats_zero, int64_t rows, int32_t D,
+                      vq_stream_t stream);
 
 /* K13: DINOv2 final norm on the patch rows (x_norm_patchtokens) and swap of the special rows for the aggregator's
  * camera_token [1,2,1,D] / register_token [1,2,R,D] ([UPSTREAM] Aggregator.forward + slice_expand_and_flatten:
@@ -292,6 +313,11 @@ typedef struct vq_block_weights {
   const void* fc2_w; /* bf16 [D, hidden] */
   const float* fc2_b;
   const float* ls2;
+  /* LayerNorm folding (0 = off: qkv_w / fc1_w are the plain weights and vq_layernorm runs before them).  When set,
+   * qkv_w = bf16(W_qkv diag(norm1_w)), qkv_b = W_qkv norm1_b + b_qkv, qkv_colsum[n] = sum_k qkv_w[n,k] (of the ROUNDED
+   * bf16 weight, f32), and likewise fc1_w / fc1_b / fc1_colsum with norm2. */
+  int32_t ln_folded;
+  const float *qkv_colsum, *fc1_colsum;
   /* upper bound of |q . k| * log2(e)/8 over all token pairs, proven from q_norm / k_norm (host side:
    * (8 max|w_q| + |b_q|_2)(8 max|w_k| + |b_k|_2) * log2(e)/8, rotation by RoPE preserves norms); 0 = unknown */
   float qk_score_bound;

@@ -46,3 +46,26 @@ def test_aggregator_matches_oracle(img, D, heads, depth, stem_depth, B, S, sens)
     n = 17
     taken = agg.encode_tokens(images.cuda(), n)
     assert torch.equal(taken, out_list[-1].reshape(B, -1, 2 * D)[:, :n])
+
+
+def test_layernorm_folding_matches_the_two_kernel_form():
+    """The LayerNorm-folded schedule (5 launches per block) against the LayerNorm-kernel schedule (7): same tokens up
+    to bf16 rounding, and both within the parity tolerance of the oracle (sensitised weights: non-trivial LN affine)."""
+    cfg = AggregatorConfig(img_size=126, embed_dim=256, num_heads=4, depth=3, stem_depth=2)
+    state = init_aggregator_state(cfg, seed=0, sensitised=True)
+    images = torch.rand(2, 2, 3, 126, 126, generator=torch.Generator().manual_seed(1))
+    ref_list, _ = aggregator_forward(state, images, cfg, return_all=False)
+    agg = _build(cfg, state)
+    from vggt_qwen3_b200 import _lib
+
+    outs = {}
+    for fold in (True, False):
+        agg.fold_layernorm = fold
+        agg.invalidate_packed()
+        n0 = _lib.lib().vq_launch_count()
+        outs[fold] = agg(images.cuda())[0][-1]
+        torch.cuda.synchronize()
+        outs[(fold, "launches")] = _lib.lib().vq_launch_count() - n0
+        assert_token_parity(outs[fold], ref_list[-1], f"fold_layernorm={fold}")
+    assert outs[(True, "launches")] < outs[(False, "launches")]
+    assert_token_parity(outs[True], outs[False].float(), "folded vs two-kernel form", cos_min=0.9995, rel_max=1.5e-2)

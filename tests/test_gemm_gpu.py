@@ -127,3 +127,66 @@ def test_gemm_dropout_epilogues(M, N, K, f32):
     out = ops.gemm(A, B, epilogue=ops.EPI_GELU_BWD, aux=pre, extra={"dropout": d})
     torch.cuda.synchronize()
     assert _rel(out, keep * ref * dgelu) < 1e-2
+
+
+def _fold(W, b, gamma, beta):
+    """Host-side folding of a LayerNorm into the Linear that consumes it (aggregator.Aggregator._pack.folded)."""
+    w16 = (W * gamma[None, :]).bfloat16().contiguous()
+    return w16, w16.float().sum(dim=1).contiguous(), (W @ beta + b).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(1374, 4096, 1024, "gelu"), (300, 512, 256, "linear"), (10992, 1024, 1024, "linear"),
+                                        (777, 3072, 1024, "qkv")])
+def test_gemm_layernorm_folded_consumer(M, N, K, mode):
+    """LayerNorm folded into the consuming GEMM: A = raw bf16 rows, W' = W diag(gamma), per-row (sum, sum of squares)
+    -> rstd (x W'^T - mean colsum(W')) + (W beta + b), against LayerNorm + Linear in fp32."""
+    from vggt_qwen3_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, K, device="cuda", generator=g) * 3.0 + 0.7            # non-zero mean, non-unit variance
+    x[:, 5] += 40.0                                                            # an outlier channel
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    gamma = 1.0 + 0.3 * torch.randn(K, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(K, device="cuda", generator=g)
+    eps = 1e-5
+    xb, stats = ops.row_stats_cast(x)
+    assert torch.equal(xb, x.bfloat16())
+    assert torch.allclose(stats[:, 0], x.sum(1), rtol=1e-5, atol=1e-2) and torch.allclose(stats[:, 1], (x * x).sum(1), rtol=1e-5)
+    w16, colsum, bias = _fold(W, b, gamma, beta)
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (K,), gamma, beta, eps), W, b)
+    extra = {"ln_stats": stats, "ln_colsum": colsum, "ln_eps": eps}
+    if mode == "gelu":
+        out = ops.gemm(xb, w16, bias=bias, epilogue=ops.EPI_GELU, extra=extra)
+        ref = torch.nn.functional.gelu(ref)
+    elif mode == "linear":
+        out = ops.gemm(xb, w16, bias=bias, extra=extra)
+    else:   # QKV epilogue without q/k norm + rope (DINOv2 stem form): bias and q scale only
+        extra.update(tokens_per_frame=M, patch_start=5, grid_w=37, apply_qknorm_rope=0, q_scale=1.0)
+        out = ops.gemm(xb, w16, bias=bias, epilogue=ops.EPI_QKV_ROPE, extra=extra)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(1374, 1024, 4096), (10992, 1024, 1024), (130, 256, 128)])
+def test_gemm_row_statistics_producer(M, N, K):
+    """proj / fc2 epilogue of a LayerNorm-folded chain: besides C = add + gamma (acc + bias) (f32, in place) it leaves the
+    bf16 copy of the new rows, their (sum, sum of squares) in `stats_out`, and clears `stats_zero`."""
+    from vggt_qwen3_b200 import ops
+
+    g, A, B, ref = _operands(M, N, K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.rand(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    expect = x + gamma * (ref + bias)
+    stats = torch.zeros(M, 2, device="cuda")
+    other = torch.full((M, 2), 7.0, device="cuda")
+    copy = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out = ops.gemm(A, B, bias=bias, gamma=gamma, add=x, out=x, out_dtype=torch.float32,
+                   extra={"stats_out": stats, "stats_zero": other, "c_copy_bf16": copy})
+    torch.cuda.synchronize()
+    assert _rel(out, expect) < 2e-3
+    assert torch.equal(copy, out.bfloat16())
+    assert torch.allclose(stats[:, 0], out.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[:, 1], (out * out).sum(1), rtol=1e-4)
+    assert other.abs().max() == 0

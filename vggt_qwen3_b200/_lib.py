@@ -53,6 +53,8 @@ class GemmDesc(C.Structure):
         ("n_patches", C.c_int32),
         ("pos_embed", _f32p),
         ("dropout", DropoutDesc),
+        ("ln_stats", _f32p), ("ln_colsum", _f32p), ("ln_eps", C.c_float),
+        ("stats_out", _f32p), ("stats_zero", _f32p), ("c_copy_bf16", C.c_void_p),
     ]
 
 
@@ -62,6 +64,7 @@ class BlockWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "norm1_w", "norm1_b", "qkv_w", "qkv_b", "q_norm_w", "q_norm_b", "k_norm_w", "k_norm_b",
         "proj_w", "proj_b", "ls1", "norm2_w", "norm2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")] + [
+        ("ln_folded", C.c_int32), ("qkv_colsum", C.c_void_p), ("fc1_colsum", C.c_void_p),
         ("qk_score_bound", C.c_float)]
 
 
@@ -185,6 +188,7 @@ _EXTRA_DECLS: dict[str, list] = {
     "vq_im2col_patches": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "vq_init_special_tokens": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "vq_layernorm": [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp],
+    "vq_row_stats_cast": [_vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "vq_stem_finalize": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
     "vq_gather_tokens": [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp],
     "vq_splice_overwrite": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp],

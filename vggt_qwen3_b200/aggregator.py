@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -114,6 +115,9 @@ class Aggregator(nn.Module):
         self.camera_token = nn.Parameter(torch.randn(1, 2, 1, embed_dim) * 1e-6)
         self.register_token = nn.Parameter(torch.randn(1, 2, num_register_tokens, embed_dim) * 1e-6)
         self.Kp = (3 * patch_size * patch_size + 7) // 8 * 8
+        # LayerNorm folded into the qkv / fc1 GEMMs (no standalone LayerNorm launches; csrc/aggregator.cu).  VQ_FOLD_LN=0
+        # keeps the two-kernel form (A/B runs, debugging); flip `fold_layernorm` + invalidate_packed() at run time.
+        self.fold_layernorm = os.environ.get("VQ_FOLD_LN", "1") != "0"
         self._packed: Optional[dict] = None
         self._workspaces: Dict[tuple, torch.Tensor] = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
@@ -130,7 +134,7 @@ class Aggregator(nn.Module):
     def _pack(self, device: torch.device, gh: int, gw: int) -> dict:
         """bf16 copies of the matrices (nn.Linear layout), f32 copies of every vector, rope tables, and the
         ctypes structs pointing at them.  Done once per (device, patch grid); weights are frozen."""
-        key = (str(device), gh, gw)
+        key = (str(device), gh, gw, self.fold_layernorm)
         if self._packed is not None and self._packed["key"] == key:
             return self._packed
         keep: List[torch.Tensor] = []
@@ -145,10 +149,26 @@ class Aggregator(nn.Module):
             keep.append(t)
             return t.data_ptr()
 
+        def folded(lin: nn.Linear, ln: nn.LayerNorm):
+            """LayerNorm folded into the Linear that consumes it (vq_gemm_desc.ln_stats): W' = bf16(W diag(gamma)),
+            colsum = row sums of the ROUNDED W' in f32 (what the tensor core multiplies), b' = W beta + b."""
+            wf = lin.weight.detach().to(device=device, dtype=torch.float32)
+            gam = ln.weight.detach().to(device=device, dtype=torch.float32)
+            bet = ln.bias.detach().to(device=device, dtype=torch.float32)
+            w16 = (wf * gam[None, :]).to(torch.bfloat16).contiguous()
+            keep.append(w16)
+            colsum = w16.float().sum(dim=1)
+            bias = wf @ bet + lin.bias.detach().to(device=device, dtype=torch.float32)
+            return w16.data_ptr(), vec(bias), vec(colsum)
+
         def block(b: _BlockParams) -> BlockWeights:
             w = BlockWeights()
             w.norm1_w, w.norm1_b = vec(b.norm1.weight), vec(b.norm1.bias)
-            w.qkv_w, w.qkv_b = mat(b.attn.qkv.weight), vec(b.attn.qkv.bias)
+            if self.fold_layernorm:
+                w.ln_folded = 1
+                w.qkv_w, w.qkv_b, w.qkv_colsum = folded(b.attn.qkv, b.norm1)
+            else:
+                w.qkv_w, w.qkv_b = mat(b.attn.qkv.weight), vec(b.attn.qkv.bias)
             if hasattr(b.attn, "q_norm"):
                 w.q_norm_w, w.q_norm_b = vec(b.attn.q_norm.weight), vec(b.attn.q_norm.bias)
                 w.k_norm_w, w.k_norm_b = vec(b.attn.k_norm.weight), vec(b.attn.k_norm.bias)
@@ -156,7 +176,10 @@ class Aggregator(nn.Module):
             w.proj_w, w.proj_b = mat(b.attn.proj.weight), vec(b.attn.proj.bias)
             w.ls1 = vec(b.ls1.gamma)
             w.norm2_w, w.norm2_b = vec(b.norm2.weight), vec(b.norm2.bias)
-            w.fc1_w, w.fc1_b = mat(b.mlp.fc1.weight), vec(b.mlp.fc1.bias)
+            if self.fold_layernorm:
+                w.fc1_w, w.fc1_b, w.fc1_colsum = folded(b.mlp.fc1, b.norm2)
+            else:
+                w.fc1_w, w.fc1_b = mat(b.mlp.fc1.weight), vec(b.mlp.fc1.bias)
             w.fc2_w, w.fc2_b = mat(b.mlp.fc2.weight), vec(b.mlp.fc2.bias)
             w.ls2 = vec(b.ls2.gamma)
             return w

@@ -22,6 +22,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct Workspace {
   float* x;
   void *xn, *qkv, *att, *h;
+  float* stats[2];   // LayerNorm-folded chain: (sum, sum of squares) per row, two buffers that ping-pong
   size_t total;
 };
 
@@ -43,6 +44,7 @@ Workspace carve(const vq_aggregator_cfg* c, void* base) {
   const size_t h_bytes = M * (size_t)c->hidden * 2;
   const size_t patch_bytes = (size_t)c->B * c->S * gh * gw * c->Kp * 2;
   const size_t o_h = take(h_bytes > patch_bytes ? h_bytes : patch_bytes);
+  const size_t o_s0 = take(M * 2 * 4), o_s1 = take(M * 2 * 4);
   Workspace w;
   char* b = reinterpret_cast<char*>(base);
   w.x = reinterpret_cast<float*>(b + o_x);
@@ -50,6 +52,8 @@ Workspace carve(const vq_aggregator_cfg* c, void* base) {
   w.qkv = b + o_qkv;
   w.att = b + o_att;
   w.h = b + o_h;
+  w.stats[0] = reinterpret_cast<float*>(b + o_s0);
+  w.stats[1] = reinterpret_cast<float*>(b + o_s1);
   w.total = off;
   return w;
 }
@@ -72,9 +76,15 @@ int run_block(const vq_aggregator_cfg* c, const vq_block_weights& bw, const vq_a
               vq_stream_t stream) {
   const int D = c->D;
   int rc;
+  // LayerNorm folded into the GEMMs (bw.ln_folded): ws.xn holds the RAW bf16 rows of x and ws.stats[0] their
+  // (sum, sum of squares); the proj epilogue rebuilds both for the MLP half into stats[1], the fc2 epilogue for the
+  // next block into stats[0].  5 launches per block instead of 7.
+  const bool fold = bw.ln_folded != 0;
   // LN1
-  rc = vq_layernorm(ws.x, VQ_F32, ws.xn, VQ_BF16, bw.norm1_w, bw.norm1_b, M, D, eps, nullptr, nullptr, stream);
-  if (rc) return rc;
+  if (!fold) {
+    rc = vq_layernorm(ws.x, VQ_F32, ws.xn, VQ_BF16, bw.norm1_w, bw.norm1_b, M, D, eps, nullptr, nullptr, stream);
+    if (rc) return rc;
+  }
   // qkv (+ QK-norm + RoPE for aggregator blocks), q pre-scaled by log2(e)/sqrt(64)
   {
     vq_gemm_desc g;
@@ -91,6 +101,7 @@ int run_block(const vq_aggregator_cfg* c, const vq_block_weights& bw, const vq_a
     g.qk_eps = c->qk_eps;
     g.q_scale = 1.4426950408889634f / 8.0f;
     g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_positions = w->rope_max_pos + 1;
+    if (fold) { g.ln_stats = ws.stats[0]; g.ln_colsum = bw.qkv_colsum; g.ln_eps = eps; }
     rc = vq_gemm(&g, stream);
     if (rc) return rc;
   }
@@ -107,12 +118,15 @@ int run_block(const vq_aggregator_cfg* c, const vq_block_weights& bw, const vq_a
     g.epilogue = VQ_EPI_LINEAR;
     g.bias = bw.proj_b; g.gamma = bw.ls1;
     g.add = ws.x; g.ldadd = D;
+    if (fold) { g.stats_out = ws.stats[1]; g.stats_zero = ws.stats[0]; g.c_copy_bf16 = ws.xn; }
     rc = vq_gemm(&g, stream);
     if (rc) return rc;
   }
   // LN2
-  rc = vq_layernorm(ws.x, VQ_F32, ws.xn, VQ_BF16, bw.norm2_w, bw.norm2_b, M, D, eps, nullptr, nullptr, stream);
-  if (rc) return rc;
+  if (!fold) {
+    rc = vq_layernorm(ws.x, VQ_F32, ws.xn, VQ_BF16, bw.norm2_w, bw.norm2_b, M, D, eps, nullptr, nullptr, stream);
+    if (rc) return rc;
+  }
   // h = gelu(xn W1^T + b1)
   {
     vq_gemm_desc g;
@@ -123,6 +137,7 @@ int run_block(const vq_aggregator_cfg* c, const vq_block_weights& bw, const vq_a
     g.C = ws.h; g.ldc = c->hidden; g.c_dtype = VQ_BF16;
     g.epilogue = VQ_EPI_GELU;
     g.bias = bw.fc1_b;
+    if (fold) { g.ln_stats = ws.stats[1]; g.ln_colsum = bw.fc1_colsum; g.ln_eps = eps; }
     rc = vq_gemm(&g, stream);
     if (rc) return rc;
   }
@@ -137,6 +152,7 @@ int run_block(const vq_aggregator_cfg* c, const vq_block_weights& bw, const vq_a
     g.epilogue = VQ_EPI_LINEAR;
     g.bias = bw.fc2_b; g.gamma = bw.ls2;
     g.add = ws.x; g.ldadd = D;
+    if (fold) { g.stats_out = ws.stats[0]; g.stats_zero = ws.stats[1]; g.c_copy_bf16 = ws.xn; }
     rc = vq_gemm(&g, stream);
     if (rc) return rc;
   }
@@ -191,6 +207,19 @@ extern "C" int vq_aggregator_forward(const vq_aggregator_cfg* c, const vq_aggreg
   }
   rc = vq_init_special_tokens(ws.x, w->cls_token, w->pos_embed, w->register_tokens, F, P, D, c->n_special, stream);
   if (rc) return rc;
+  // every block of a chain must agree on the folding (the statistics are handed from block to block)
+  bool fold_stem = w->n_stem > 0, fold_agg = true;
+  for (int i = 0; i < w->n_stem; ++i) fold_stem = fold_stem && w->stem_blocks[i].ln_folded;
+  for (int i = 0; i < w->depth; ++i) fold_agg = fold_agg && w->frame_blocks[i].ln_folded && w->global_blocks[i].ln_folded;
+  for (int i = 0; i < w->n_stem; ++i)
+    VQ_CHECK_ARG((w->stem_blocks[i].ln_folded != 0) == fold_stem, "stem blocks disagree on ln_folded");
+  for (int i = 0; i < w->depth; ++i)
+    VQ_CHECK_ARG((w->frame_blocks[i].ln_folded != 0) == fold_agg && (w->global_blocks[i].ln_folded != 0) == fold_agg,
+                 "aggregator blocks disagree on ln_folded");
+  if (fold_stem) {
+    rc = vq_row_stats_cast(ws.x, ws.xn, ws.stats[0], ws.stats[1], M, D, stream);
+    if (rc) return rc;
+  }
   for (int i = 0; i < w->n_stem; ++i) {
     rc = run_block(c, w->stem_blocks[i], w, ws, M, P, gw, F, P, c->stem_eps, stream);
     if (rc) return rc;
@@ -198,6 +227,11 @@ extern "C" int vq_aggregator_forward(const vq_aggregator_cfg* c, const vq_aggreg
   rc = vq_stem_finalize(ws.x, w->stem_norm_w, w->stem_norm_b, w->camera_token, w->register_token, M, D, P, c->S,
                         c->n_special, c->stem_eps, stream);
   if (rc) return rc;
+
+  if (fold_agg) {
+    rc = vq_row_stats_cast(ws.x, ws.xn, ws.stats[0], ws.stats[1], M, D, stream);
+    if (rc) return rc;
+  }
 
   // ---- alternating attention
   const long long SP = (long long)c->S * P;

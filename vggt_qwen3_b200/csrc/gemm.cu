@@ -53,6 +53,14 @@ struct GemmArgs {
   int n_patches;
   const float* pos_embed;
   DropoutParams drop;  // thr == 0: off
+  // LayerNorm folding (see vq_gemm_desc): consumer side (A holds the RAW rows, the norm is applied in the epilogue) ...
+  const float* ln_stats;   // [M][2] (sum x, sum x^2) of the rows of A, or null
+  const float* ln_colsum;  // [N] row sums of the (gamma-folded) weight
+  float ln_eps, ln_inv_dim;
+  // ... and producer side (LINEAR f32 epilogue): row statistics and a bf16 copy of the rows it writes
+  float* stats_out;        // [M][2], accumulated with atomics, or null
+  float* stats_zero;       // [M][2] cleared by this launch after its grid dependency resolved, or null
+  void* c_copy;            // bf16 [M, ldc] copy of C, or null
 };
 
 // CG = CTAs per MMA (cta_group): 1 = one CTA owns a 128 x BLOCK_N tile; 2 = a CTA pair owns a 256 x BLOCK_N tile,
@@ -382,6 +390,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     };
     prefetch_add(first_tile);
+    if constexpr (MODE == VQ_EPI_LINEAR && OUT_F32) {
+      // the statistics buffer of the NEXT producer: its last readers finished before this grid's dependency resolved
+      if (g.stats_zero) {
+        const int n2 = 2 * g.M;
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < n2; i += gridDim.x * 256) g.stats_zero[i] = 0.f;
+      }
+    }
     int it = 0;
     for (int tile = first_tile; tile < g.total_tiles; tile += tile_stride, ++it) {
       prefetch_add(tile + tile_stride);
@@ -402,6 +417,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (n_base + c < g.N) {
           if (g.bias) b = __ldg(reinterpret_cast<const float4*>(g.bias + n_base + c));
           if (g.gamma) gm = __ldg(reinterpret_cast<const float4*>(g.gamma + n_base + c));
+          else if (g.ln_colsum) gm = __ldg(reinterpret_cast<const float4*>(g.ln_colsum + n_base + c));
         }
         *reinterpret_cast<float4*>(my_vec + c) = b;
         *reinterpret_cast<float4*>(my_vec + kHalfN + c) = gm;
@@ -425,15 +441,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (n_head >= g.N) break;
           float v[64];
           {
+            // LayerNorm folded into this GEMM: A held the raw rows x, W the gamma-scaled weight W', so
+            // LN(x) W^T + b = rstd (x W'^T - mean colsum(W')) + (W beta + b); the last term arrives as the bias
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if (g.ln_stats && row_ok) {
+              const float2 st = *reinterpret_cast<const float2*>(g.ln_stats + 2 * (long long)m);
+              ln_mean = st.x * g.ln_inv_dim;
+              ln_rstd = rsqrtf(fmaxf(st.y * g.ln_inv_dim - ln_mean * ln_mean, 0.f) + g.ln_eps);
+            }
+            const float* cs = my_vec + kHalfN + hh * 64;
             uint32_t r[32];
             tmem_ld32(taddr + hh * 64, r);
             tmem_wait_ld();
+            if (g.ln_stats) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + my_vec[hh * 64 + i];
+              for (int i = 0; i < 32; ++i)
+                v[i] = (__uint_as_float(r[i]) - ln_mean * cs[i]) * ln_rstd + my_vec[hh * 64 + i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + my_vec[hh * 64 + i];
+            }
             tmem_ld32(taddr + hh * 64 + 32, r);
             tmem_wait_ld();
+            if (g.ln_stats) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]) + my_vec[hh * 64 + 32 + i];
+              for (int i = 0; i < 32; ++i)
+                v[32 + i] = (__uint_as_float(r[i]) - ln_mean * cs[32 + i]) * ln_rstd + my_vec[hh * 64 + 32 + i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]) + my_vec[hh * 64 + 32 + i];
+            }
           }
           const int which = n_head / D3;  // 0 = q, 1 = k, 2 = v
           if (which < 2 && g.apply_qknorm_rope) {
@@ -532,6 +569,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int rsub = lane / kLanesPerRow;
         const int m_warp0 = m_blk * kTileM + (int)cta_rank * kBlockM + quarter * 32;
         constexpr int kChunks = kHalfN / 32;
+        // LayerNorm folding, consumer side: per-row mean / rstd of the rows this thread touches
+        float ln_mean[kPasses], ln_rstd[kPasses];
+        if constexpr (MODE == VQ_EPI_GELU || MODE == VQ_EPI_LINEAR) {
+          if (g.ln_stats) {
+#pragma unroll
+            for (int ps = 0; ps < kPasses; ++ps) {
+              const int mr = m_warp0 + ps * kRowsPerPass + rsub;
+              float2 st = make_float2(0.f, 1.f);
+              if (mr < g.M) st = *reinterpret_cast<const float2*>(g.ln_stats + 2 * (long long)mr);
+              ln_mean[ps] = st.x * g.ln_inv_dim;
+              ln_rstd[ps] = rsqrtf(fmaxf(st.y * g.ln_inv_dim - ln_mean[ps] * ln_mean[ps], 0.f) + g.ln_eps);
+            }
+          }
+        }
+        // producer side: running (sum, sum of squares) of the rows this thread writes, over this warp's columns
+        float rs[kPasses], rq[kPasses];
+#pragma unroll
+        for (int ps = 0; ps < kPasses; ++ps) rs[ps] = rq[ps] = 0.f;
         uint32_t acc[2][32];
         if (n_base < g.N) tmem_ld32(taddr, acc[0]);
 #pragma unroll
@@ -592,6 +647,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[e + 2] = a4.z * g.alpha + bv[e + 2];
               v[e + 3] = a4.w * g.alpha + bv[e + 3];
             }
+            if constexpr (MODE == VQ_EPI_GELU || MODE == VQ_EPI_LINEAR) {
+              if (g.ln_stats) {   // LN(x) W^T + b = rstd (x W'^T - mean colsum(W')) + b'   (gv = colsum, bv = b')
+#pragma unroll
+                for (int e = 0; e < kVec; ++e)
+                  v[e] = (v[e] - bv[e] - ln_mean[ps] * gv[e]) * ln_rstd[ps] + bv[e];
+              }
+            }
             if (!ok[ps]) continue;
             if constexpr (MODE == VQ_EPI_GELU) {
               if (g.aux) storev<false>(g.aux, orow[ps] * g.ldaux + c_c + ncol, v);
@@ -630,6 +692,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int e = 0; e < kVec; ++e) v[e] += addv[ps][e];
             }
             storev<OUT_F32>(g.C, orow[ps] * g.ldc + c_c + ncol, v);
+            if constexpr (MODE == VQ_EPI_LINEAR && OUT_F32) {
+              if (g.c_copy) {      // bf16 copy of the rows: the A operand of the LayerNorm-folded GEMM that follows
+                uint2 u;
+                u.x = pack_bf16x2(v[0], v[1]);
+                u.y = pack_bf16x2(v[2], v[3]);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.c_copy) + orow[ps] * g.ldc + c_c + ncol) = u;
+              }
+              if (g.stats_out) {
+                rs[ps] += (v[0] + v[1]) + (v[2] + v[3]);
+                rq[ps] += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+              }
+            }
+          }
+        }
+        if constexpr (MODE == VQ_EPI_LINEAR && OUT_F32) {
+          if (g.stats_out) {
+            // the kLanesPerRow lanes that share a row combine, then one pair of atomics per row and warp
+#pragma unroll
+            for (int ps = 0; ps < kPasses; ++ps) {
+              float a = rs[ps], b = rq[ps];
+#pragma unroll
+              for (int o = kLanesPerRow / 2; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+              }
+              const int mr = m_warp0 + ps * kRowsPerPass + rsub;
+              if ((lane % kLanesPerRow) == 0 && mr < g.M && n_base < g.N) {
+                atomicAdd(g.stats_out + 2 * (long long)mr, a);
+                atomicAdd(g.stats_out + 2 * (long long)mr + 1, b);
+              }
+            }
           }
         }
       }
@@ -812,6 +905,20 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
                                                        d->epilogue == VQ_EPI_GELU_BWD)),
                "dropout: unbatched LINEAR / GELU / GELU_BWD epilogues only");
   g.drop = make_dropout_params(d->dropout.p, d->dropout.seed, d->dropout.offset, d->dropout.site);
+  VQ_CHECK_ARG((d->ln_stats == nullptr) == (d->ln_colsum == nullptr), "ln_stats and ln_colsum go together");
+  VQ_CHECK_ARG(!d->ln_stats || (Z0 * Z1 == 1 && !d->gamma && d->bias && !d->a_major &&
+                                (d->epilogue == VQ_EPI_LINEAR || d->epilogue == VQ_EPI_GELU ||
+                                 d->epilogue == VQ_EPI_QKV_ROPE)),
+               "LayerNorm folding: unbatched K-major A, bias required, no gamma, LINEAR / GELU / QKV_ROPE epilogue");
+  VQ_CHECK_ARG(!d->ln_colsum || (reinterpret_cast<uintptr_t>(d->ln_colsum) % 16) == 0, "ln_colsum alignment");
+  VQ_CHECK_ARG(!d->ln_stats || (reinterpret_cast<uintptr_t>(d->ln_stats) % 8) == 0, "ln_stats alignment");
+  VQ_CHECK_ARG(!(d->stats_out || d->stats_zero || d->c_copy_bf16) ||
+                   (Z0 * Z1 == 1 && d->epilogue == VQ_EPI_LINEAR && d->c_dtype == VQ_F32),
+               "row statistics / bf16 copy: unbatched LINEAR epilogue with f32 output only");
+  VQ_CHECK_ARG(!d->c_copy_bf16 || (reinterpret_cast<uintptr_t>(d->c_copy_bf16) % 8) == 0, "c_copy_bf16 alignment");
+  g.ln_stats = d->ln_stats; g.ln_colsum = d->ln_colsum;
+  g.ln_eps = d->ln_eps; g.ln_inv_dim = 1.0f / (float)d->K;
+  g.stats_out = d->stats_out; g.stats_zero = d->stats_zero; g.c_copy = d->c_copy_bf16;
 
   const bool f32 = d->c_dtype == VQ_F32;
   switch (d->epilogue) {

@@ -146,6 +146,40 @@ layernorm_kernel(const void* __restrict__ in, void* __restrict__ out, const floa
   }
 }
 
+// Entry of a LayerNorm-folded chain: per-row (sum, sum of squares) + bf16 copy, one warp per row.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+row_stats_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ stats,
+                      float* __restrict__ stats_zero, long long rows, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[VEC][4];
+  load_row<VEC, true>(x, row, D, lane, v);
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    q += (v[i][0] * v[i][0] + v[i][1] * v[i][1]) + (v[i][2] * v[i][2] + v[i][3] * v[i][3]);
+    uint2 u;
+    u.x = pack_bf16x2(v[i][0], v[i][1]);
+    u.y = pack_bf16x2(v[i][2], v[i][3]);
+    *reinterpret_cast<uint2*>(xb + row * D + (i * 32 + lane) * 4) = u;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    stats[2 * row] = s;
+    stats[2 * row + 1] = q;
+    if (stats_zero) {
+      stats_zero[2 * row] = 0.f;
+      stats_zero[2 * row + 1] = 0.f;
+    }
+  }
+}
+
 // K13: DINOv2 final LayerNorm on the patch rows (in place, f32) + camera/register tokens swapped into
 // the special rows (token index 0 for the first frame of a scene, 1 for the others).
 template <int VEC>
@@ -293,6 +327,31 @@ extern "C" int vq_layernorm(const void* in, int32_t in_dtype, void* out, int32_t
   if (i32 && o32) return launch_ln<true, true>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
   if (!i32 && !o32) return launch_ln<false, false>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
   return launch_ln<false, true>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
+}
+
+extern "C" int vq_row_stats_cast(const float* x, void* xb_bf16, float* stats, float* stats_zero, int64_t rows, int32_t D,
+                                 vq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(x && xb_bf16 && stats, "null pointer");
+  VQ_CHECK_ARG(rows > 0 && D > 0 && D % 128 == 0, "rows > 0 and D % 128 == 0 required");
+  const int warps = 8;
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(xb_bf16);
+  LaunchScope scope(kKindRow, "row_stats_cast", (int)rows, D, 0, 0, (double)rows * D * 6.0, stream);
+#define VQ_RS_CASE(V)                                                                                              \
+  case V:                                                                                                          \
+    VQ_CHECK_CUDA(launch_pdl(row_stats_cast_kernel<V>, dim3(grid), dim3(warps * 32), 0, stream, x, xb, stats,      \
+                             stats_zero, (long long)rows, D));                                                     \
+    break;
+  switch (D / 128) {
+    VQ_RS_CASE(1) VQ_RS_CASE(2) VQ_RS_CASE(3) VQ_RS_CASE(4) VQ_RS_CASE(6) VQ_RS_CASE(8)
+    default:
+      set_error("row_stats_cast: unsupported width");
+      return VQ_ERR_UNSUPPORTED;
+  }
+#undef VQ_RS_CASE
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
 }
 
 extern "C" int vq_stem_finalize(float* x, const float* gamma, const float* beta, const float* camera_token,

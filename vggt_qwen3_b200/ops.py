@@ -172,6 +172,19 @@ def dropout_mask(rows: int, cols: int, ld: int, p: float, seed: int, offset: int
     return keep
 
 
+def row_stats_cast(x: torch.Tensor, stats_zero: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(xb = bf16(x), stats f32 [rows, 2] = per-row (sum, sum of squares)) of an f32 [rows, D] tensor: the entry of a
+    LayerNorm-folded GEMM chain (vq_gemm_desc.ln_stats); `stats_zero` (f32 [rows, 2]) is cleared in the same launch."""
+    _req(x, torch.float32, "x")
+    assert x.dim() == 2 and x.is_contiguous()
+    rows, D = x.shape
+    xb = torch.empty(rows, D, device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().vq_row_stats_cast(x.data_ptr(), xb.data_ptr(), stats.data_ptr(), _ptr(stats_zero), rows, D,
+                                            _stream()), "vq_row_stats_cast")
+    return xb, stats
+
+
 def layernorm_bwd(dy: torch.Tensor, z: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
                   dropout: Optional["_lib.DropoutDesc"] = None):
     """Returns (dz bf16, dgamma f32, dbeta f32) for bf16 dy and saved LN input z; with `dropout` additionally the
