@@ -115,9 +115,12 @@ class Aggregator(nn.Module):
         self.camera_token = nn.Parameter(torch.randn(1, 2, 1, embed_dim) * 1e-6)
         self.register_token = nn.Parameter(torch.randn(1, 2, num_register_tokens, embed_dim) * 1e-6)
         self.Kp = (3 * patch_size * patch_size + 7) // 8 * 8
-        # LayerNorm folded into the qkv / fc1 GEMMs (no standalone LayerNorm launches; csrc/aggregator.cu).  VQ_FOLD_LN=0
-        # keeps the two-kernel form (A/B runs, debugging); flip `fold_layernorm` + invalidate_packed() at run time.
-        self.fold_layernorm = os.environ.get("VQ_FOLD_LN", "1") != "0"
+        # Optional: LayerNorm folded into the qkv / fc1 GEMMs (no standalone LayerNorm launches; csrc/aggregator.cu).
+        # OFF by default: measured on B200 (round 2) the K = 1024 GEMMs are epilogue-issue-bound, so the folded arithmetic
+        # costs more there (+47 us per block at c2) than the two LayerNorm launches it removes (33 us), and the f32
+        # atomics of the row statistics make the result run-to-run non-bit-identical.  VQ_FOLD_LN=1 or
+        # `fold_layernorm = True` + invalidate_packed() selects it (parity-tested both ways).
+        self.fold_layernorm = os.environ.get("VQ_FOLD_LN", "0") == "1"
         self._packed: Optional[dict] = None
         self._workspaces: Dict[tuple, torch.Tensor] = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
