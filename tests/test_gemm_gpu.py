@@ -190,3 +190,40 @@ def test_gemm_row_statistics_producer(M, N, K):
     assert torch.allclose(stats[:, 0], out.sum(1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(stats[:, 1], (out * out).sum(1), rtol=1e-4)
     assert other.abs().max() == 0
+
+
+@pytest.mark.parametrize("M,N,K,mode", [
+    (10992, 1024, 4096, "lsres"),     # c2 fc2: 172 pair tiles on 74 pairs -> 24 tail tiles, 3 K slices each
+    (10992, 4096, 1024, "gelu"),      # c2 fc1: 22 tail tiles, 3 slices of 5-6 k-blocks
+    (1024, 16384, 4096, "gelu"),      # Perceiver fc1: 34 tail tiles, 2 slices
+    (512, 4096, 2048, "linear"),      # fewer tiles than CTA pairs: every tile is a (split) tail tile
+    (640, 512, 8192, "linear"),       # 6 tiles, 4 slices each
+    (300, 256, 1024, "linear_f32"),   # single-CTA tiles (128 x 128), split tail
+])
+def test_gemm_k_sliced_tail_tiles(M, N, K, mode):
+    """Tail tiles of the persistent schedule split along K across otherwise idle CTAs: same values as the unsplit
+    schedule up to fp32 summation order, and bit-identical from run to run (partials are added in slice order)."""
+    from vggt_qwen3_b200 import ops
+
+    g, A, B, ref = _operands(M, N, K)
+    bias = torch.randn(N, device="cuda", generator=g)
+
+    def run():
+        if mode == "lsres":
+            gamma = torch.full((N,), 0.5, device="cuda")
+            x = torch.ones(M, N, device="cuda")
+            return ops.gemm(A, B, bias=bias, gamma=gamma, add=x, out=x, out_dtype=torch.float32), 1.0 + 0.5 * (ref + bias)
+        if mode == "gelu":
+            return ops.gemm(A, B, bias=bias, epilogue=ops.EPI_GELU), torch.nn.functional.gelu(ref + bias)
+        if mode == "linear_f32":
+            return ops.gemm(A, B, bias=bias, out_dtype=torch.float32), ref + bias
+        return ops.gemm(A, B, bias=bias), ref + bias
+
+    out1, want = run()
+    out1 = out1.clone()
+    torch.cuda.synchronize()
+    assert _rel(out1, want) < (2e-3 if out1.dtype == torch.float32 else 1e-2)
+    for _ in range(3):
+        out2, _ = run()
+        torch.cuda.synchronize()
+        assert torch.equal(out1, out2), "K-sliced tail is not run-to-run deterministic"

@@ -107,6 +107,42 @@ bool get_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t
   return true;
 }
 
+cudaError_t splitk_workspace(cudaStream_t stream, size_t bytes, size_t n_flags, void** ws, unsigned** flags) {
+  struct Slot { void* ws = nullptr; size_t bytes = 0; unsigned* flags = nullptr; size_t n_flags = 0; };
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, Slot> slots;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t key = (reinterpret_cast<uint64_t>(stream) << 6) ^ (uint64_t)(dev & 63);
+  std::lock_guard<std::mutex> lock(mu);
+  Slot& s = slots[key];
+  if (s.bytes < bytes) {
+    if (s.ws) {
+      if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+      cudaFree(s.ws);
+      s.ws = nullptr; s.bytes = 0;
+    }
+    const size_t want = bytes < (size_t(20) << 20) ? (size_t(20) << 20) : bytes;
+    if ((e = cudaMalloc(&s.ws, want)) != cudaSuccess) return e;
+    s.bytes = want;
+  }
+  if (s.n_flags < n_flags) {
+    if (s.flags) {
+      if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+      cudaFree(s.flags);
+      s.flags = nullptr; s.n_flags = 0;
+    }
+    const size_t want = n_flags < 1024 ? 1024 : n_flags;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&s.flags), want * sizeof(unsigned))) != cudaSuccess) return e;
+    if ((e = cudaMemset(s.flags, 0, want * sizeof(unsigned))) != cudaSuccess) return e;
+    s.n_flags = want;
+  }
+  *ws = s.ws;
+  *flags = s.flags;
+  return cudaSuccess;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("VQ_PDL");

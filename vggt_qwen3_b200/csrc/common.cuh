@@ -42,6 +42,11 @@ int num_sms();   // of the current device
 // set once per (device, function); thread-safe.
 cudaError_t ensure_dynamic_smem(const void* func, int bytes, bool max_carveout = false);
 
+// Library-owned scratch for the GEMM's K-sliced tail tiles, one per (device, stream) so that launches on different
+// streams never share it: `bytes` of partial accumulators + `n_flags` zero-initialised counters (re-armed by the
+// kernel itself).  Grown on demand (the old buffer is released after the stream has drained).
+cudaError_t splitk_workspace(cudaStream_t stream, size_t bytes, size_t n_flags, void** ws, unsigned** flags);
+
 // Programmatic dependent launch (VQ_PDL=0 disables it): kernels of the hot chain (GEMM, attention, LayerNorm) are
 // launched with cudaLaunchAttributeProgrammaticStreamSerialization so that their prologue (barrier init, TMEM
 // allocation, descriptor prefetch) overlaps the tail of the previous kernel; see pdl_wait() in ptx.cuh.

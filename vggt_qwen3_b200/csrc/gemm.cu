@@ -61,7 +61,32 @@ struct GemmArgs {
   float* stats_out;        // [M][2], accumulated with atomics, or null
   float* stats_zero;       // [M][2] cleared by this launch after its grid dependency resolved, or null
   void* c_copy;            // bf16 [M, ldc] copy of C, or null
+  // Tail split (see launch_gemm_cg): tiles [0, full_tiles) are processed whole, round-robin; each of the remaining
+  // tiles is split along K into `tail_split` slices handled by different CTAs (pairs) in the last round.
+  int full_tiles, tail_split;
+  float* splitk_ws;         // partial accumulators of the slices > 0
+  unsigned* splitk_flags;   // per tail tile: [arrivals of the partial writers, owner warps done]
 };
+
+// One unit of work of a persistent CTA (pair): a whole tile or one K slice of a tail tile.
+struct GemmWork {
+  int tile, kb0, kb1, slice;   // slice < 0: whole tile
+};
+__device__ __forceinline__ bool gemm_work(const GemmArgs& g, int it, int first, int stride, int num_kb, GemmWork& w) {
+  const int n_full_iters = g.full_tiles / stride;
+  if (it < n_full_iters) {
+    w.tile = first + it * stride; w.kb0 = 0; w.kb1 = num_kb; w.slice = -1;
+    return true;
+  }
+  const int n_tail = g.total_tiles - g.full_tiles;
+  if (it > n_full_iters || first >= n_tail * g.tail_split) return false;
+  w.tile = g.full_tiles + first / g.tail_split;
+  if (g.tail_split == 1) { w.kb0 = 0; w.kb1 = num_kb; w.slice = -1; return true; }
+  w.slice = first % g.tail_split;
+  w.kb0 = w.slice * num_kb / g.tail_split;
+  w.kb1 = (w.slice + 1) * num_kb / g.tail_split;
+  return true;
+}
 
 // CG = CTAs per MMA (cta_group): 1 = one CTA owns a 128 x BLOCK_N tile; 2 = a CTA pair owns a 256 x BLOCK_N tile,
 // each CTA loading its 128 rows of A and BLOCK_N/2 rows of B.
@@ -270,7 +295,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         else tma_load_2d(dst, map, bar, c0, c1);
       };
       constexpr int kBRows = BLOCK_N / CG;  // rows (N indices) of B this CTA loads
-      for (int tile = first_tile; tile < g.total_tiles; tile += tile_stride) {
+      GemmWork wk;
+      for (int wi = 0; gemm_work(g, wi, first_tile, tile_stride, num_kb, wk); ++wi) {
+        const int tile = wk.tile;
         const int z = tile / tiles_per_z;
         const int rem = tile - z * tiles_per_z;
         const int m_blk = rem / g.n_tiles;
@@ -280,7 +307,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int b_r = z0 * g.b_r0 + z1 * g.b_r1, b_c = z0 * g.b_c0 + z1 * g.b_c1;
         const int m0 = m_blk * kTileM + (int)cta_rank * kBlockM;       // first A row of this CTA
         const int n0 = n_blk * BLOCK_N + (int)cta_rank * kBRows;       // first B row of this CTA
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;
           // the leader's barrier collects the bytes of both CTAs
@@ -321,14 +348,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint64_t desc_b0 = make_smem_desc(smem_b, b_lbo, 1024);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = first_tile; tile < g.total_tiles; tile += tile_stride, ++it) {
+      GemmWork wk;
+      for (int it = 0; gemm_work(g, it, first_tile, tile_stride, num_kb, wk); ++it) {
         const int as = it & 1;
         const uint32_t as_phase = (it >> 1) & 1;
         mbar_wait(bar_tempty + 8 * as, as_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           mbar_wait_fast(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint64_t desc_a = desc_a0 + (uint64_t)(stage * (kATileBytes >> 4));
@@ -338,8 +365,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               const uint64_t adesc = desc_a + (uint64_t)(k * a_kstep);
               const uint64_t bdesc = desc_b + (uint64_t)(k * b_kstep);
-              if constexpr (CG == 2) umma_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
-              else umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+              if constexpr (CG == 2) umma_ss_pair(d_tmem, adesc, bdesc, idesc, ((kb - wk.kb0) | k) ? 1u : 0u);
+              else umma_ss(d_tmem, adesc, bdesc, idesc, ((kb - wk.kb0) | k) ? 1u : 0u);
             }
             // frees the smem stage (in both CTAs of a pair) when these MMAs retire
             if constexpr (CG == 2) umma_commit_pair(bar_empty + 8 * stage);
@@ -389,7 +416,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (m < g.M && n < g.N) prefetch_l2(base + ((c_r + m) * g.ldadd + c_c + n) * (OUT_F32 ? 4 : 2));
       }
     };
-    prefetch_add(first_tile);
+    {
+      GemmWork w0;
+      if (gemm_work(g, 0, first_tile, tile_stride, num_kb, w0) && w0.slice <= 0) prefetch_add(w0.tile);
+    }
     if constexpr (MODE == VQ_EPI_LINEAR && OUT_F32) {
       // the statistics buffer of the NEXT producer: its last readers finished before this grid's dependency resolved
       if (g.stats_zero) {
@@ -397,9 +427,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int i = blockIdx.x * 256 + threadIdx.x; i < n2; i += gridDim.x * 256) g.stats_zero[i] = 0.f;
       }
     }
-    int it = 0;
-    for (int tile = first_tile; tile < g.total_tiles; tile += tile_stride, ++it) {
-      prefetch_add(tile + tile_stride);
+    GemmWork wk, wk_next;
+    for (int it = 0; gemm_work(g, it, first_tile, tile_stride, num_kb, wk); ++it) {
+      const int tile = wk.tile;
+      if (gemm_work(g, it + 1, first_tile, tile_stride, num_kb, wk_next) && wk_next.slice <= 0) prefetch_add(wk_next.tile);
       const int z = tile / tiles_per_z;
       const int rem = tile - z * tiles_per_z;
       const int m_blk = rem / g.n_tiles;
@@ -588,6 +619,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int ps = 0; ps < kPasses; ++ps) rs[ps] = rq[ps] = 0.f;
         uint32_t acc[2][32];
+        // K-sliced tail tile: slices > 0 park their raw accumulators in the workspace (thread-private layout: the owner's
+        // thread at the same position reads them back), slice 0 waits for them and adds them in slice order before its
+        // epilogue -- a fixed summation order, so the result does not depend on timing.
+        const int tail_idx = tile - g.full_tiles;
+        constexpr int kWarpWs = kChunks * 1024;   // floats per warp and partial tile
+        if (wk.slice > 0) {
+          float* wsp = g.splitk_ws +
+                       ((((size_t)tail_idx * (g.tail_split - 1) + (wk.slice - 1)) * CG + cta_rank) * 8 + warp) * kWarpWs;
+          if (n_base < g.N) tmem_ld32(taddr, acc[0]);
+#pragma unroll
+          for (int ch = 0; ch < kChunks; ++ch) {
+            if (n_base + ch * 32 >= g.N) break;
+            tmem_wait_ld();
+            if (ch + 1 < kChunks && n_base + (ch + 1) * 32 < g.N) tmem_ld32(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);
+            const uint32_t(&r)[32] = acc[ch & 1];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<uint4*>(wsp + ch * 1024 + lane * 32 + 4 * k) =
+                  make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+          }
+          __threadfence();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            atomicAdd(g.splitk_flags + 2 * tail_idx, 1u);
+            if constexpr (CG == 2) mbar_arrive_leader(bar_tempty + 8 * as);
+            else mbar_arrive(bar_tempty + 8 * as);
+          }
+          continue;
+        }
+        const bool owner = wk.slice == 0;
+        if (owner) {
+          if (lane == 0) {
+            const unsigned want = (unsigned)(g.tail_split - 1) * CG * 8;
+            unsigned spins = 0;
+            while (*reinterpret_cast<volatile unsigned*>(g.splitk_flags + 2 * tail_idx) < want) {
+              __nanosleep(64);
+              if (++spins > (1u << 24)) __trap();   // a partial writer never arrived
+            }
+            __threadfence();
+          }
+          __syncwarp();
+        }
         if (n_base < g.N) tmem_ld32(taddr, acc[0]);
 #pragma unroll
         for (int ch = 0; ch < kChunks; ++ch) {
@@ -595,6 +669,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (n0 >= g.N) break;  // warp-uniform
           tmem_wait_ld();
           if (ch + 1 < kChunks && n0 + 32 < g.N) tmem_ld32(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);
+          if (owner) {
+            for (int sl = 1; sl < g.tail_split; ++sl) {
+              const float* wsp = g.splitk_ws +
+                                 ((((size_t)tail_idx * (g.tail_split - 1) + (sl - 1)) * CG + cta_rank) * 8 + warp) * kWarpWs +
+                                 ch * 1024 + lane * 32;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 pv = __ldcg(reinterpret_cast<const float4*>(wsp + 4 * k));
+                uint32_t(&ra)[32] = acc[ch & 1];
+                ra[4 * k] = __float_as_uint(__uint_as_float(ra[4 * k]) + pv.x);
+                ra[4 * k + 1] = __float_as_uint(__uint_as_float(ra[4 * k + 1]) + pv.y);
+                ra[4 * k + 2] = __float_as_uint(__uint_as_float(ra[4 * k + 2]) + pv.z);
+                ra[4 * k + 3] = __float_as_uint(__uint_as_float(ra[4 * k + 3]) + pv.w);
+              }
+            }
+          }
           const uint32_t(&r)[32] = acc[ch & 1];
           __syncwarp();  // previous chunk's transposed reads are done
 #pragma unroll
@@ -726,6 +816,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      if constexpr (MODE != VQ_EPI_QKV_ROPE) {
+        if (wk.slice == 0) {   // the last owner warp to finish re-arms the tile's flags for the next launch
+          __syncwarp();
+          if (lane == 0) {
+            const int tail_idx = tile - g.full_tiles;
+            if (atomicAdd(g.splitk_flags + 2 * tail_idx + 1, 1u) == (unsigned)(CG * 8 - 1)) {
+              g.splitk_flags[2 * tail_idx] = 0u;
+              g.splitk_flags[2 * tail_idx + 1] = 0u;
+            }
+          }
+        }
+      }
       // release the accumulator stage back to the (leader's) MMA warp
       tc_fence_before();
       __syncwarp();
@@ -752,13 +854,40 @@ static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmAr
   auto kern = gemm_kernel<BLOCK_N, MODE, OUT_F32, CG>;
   VQ_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes));
   const int sms = num_sms();
-  int grid;
-  if (CG == 2) {
-    const int pairs = sms / 2;
-    grid = 2 * (g.total_tiles < pairs ? g.total_tiles : pairs);
-  } else {
-    grid = g.total_tiles < sms ? g.total_tiles : sms;
+  const int units = CG == 2 ? sms / 2 : sms;                     // CTAs (pairs) of a persistent grid
+  int grid_units = g.total_tiles < units ? g.total_tiles : units;
+  // Wave quantisation: the last round of a static round-robin schedule runs R = tiles mod units tiles on `units`
+  // CTAs (pairs).  When R leaves at least half of them idle, every tail tile is split along K into floor(units / R)
+  // slices (<= 4, >= 4 k-blocks each) that different CTAs work on concurrently; slice 0 adds the partial accumulators
+  // of the others in slice order (deterministic) before its epilogue.  c2 fc2: 172 tiles on 74 pairs = 3 rounds -> 2.33.
+  g.full_tiles = g.total_tiles / units * units;
+  g.tail_split = 1;
+  g.splitk_ws = nullptr;
+  g.splitk_flags = nullptr;
+  const int n_tail = g.total_tiles - g.full_tiles;
+  static const int split_on = [] {
+    const char* e = getenv("VQ_GEMM_TAIL_SPLIT");
+    return e ? atoi(e) : 1;
+  }();
+  if (MODE != VQ_EPI_QKV_ROPE && split_on && n_tail > 0 && g.total_tiles == g.m_tiles * g.n_tiles) {
+    const int num_kb = (g.K + kBlockK - 1) / kBlockK;
+    int split = units / n_tail;
+    if (split > 4) split = 4;
+    while (split > 1 && num_kb / split < 4) --split;
+    constexpr size_t kTileWsFloats = (size_t)CG * 8 * (BLOCK_N / 2 / 32) * 1024;
+    const size_t need = (size_t)n_tail * (split - 1) * kTileWsFloats * sizeof(float);
+    if (split > 1) {
+      void* ws = nullptr;
+      unsigned* flags = nullptr;
+      if (splitk_workspace(stream, need, (size_t)n_tail * 2, &ws, &flags) == cudaSuccess) {
+        g.tail_split = split;
+        g.splitk_ws = reinterpret_cast<float*>(ws);
+        g.splitk_flags = flags;
+        if (n_tail * split > grid_units) grid_units = n_tail * split;   // fewer tiles than CTAs: still one slice each
+      }
+    }
   }
+  const int grid = CG * grid_units;
   static const char* const kTags[] = {"gemm_linear", "gemm_gelu", "gemm_gelu_bwd", "gemm_qkv_rope", "gemm_patch"};
   const double Z = (double)g.total_tiles / ((double)g.m_tiles * g.n_tiles);
   const double mnk = (double)g.M * g.N * g.K;
