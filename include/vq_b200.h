@@ -147,6 +147,9 @@ typedef struct vq_gemm_desc {
 } vq_gemm_desc;
 
 int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream);
+/* Tuning / A-B switch (process-wide; negative = keep): maximum number of K slices a tail tile of the persistent
+ * schedule is split into (0 or 1 = never split = default; env VQ_GEMM_TAIL_SPLIT).  Measured not to pay on B200. */
+int vq_gemm_tune(int32_t tail_split_max);
 
 /* ------------------------------------------------------------------------------------------------
  * vq_attention_fwd — non-causal softmax(QK^T)V for head_dim 64 over a packed qkv buffer.

@@ -155,6 +155,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vq_num_sms.restype = C.c_int
     lib.vq_gemm.restype = C.c_int
     lib.vq_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    lib.vq_gemm_tune.restype = C.c_int
+    lib.vq_gemm_tune.argtypes = [C.c_int32]
     lib.vq_attention_fwd.restype = C.c_int
     lib.vq_attention_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.vq_attention_tune.restype = C.c_int

@@ -620,7 +620,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int ps = 0; ps < kPasses; ++ps) rs[ps] = rq[ps] = 0.f;
         uint32_t acc[2][32];
         // K-sliced tail tile: slices > 0 park their raw accumulators in the workspace (thread-private layout: the owner's
-        // thread at the same position reads them back), slice 0 waits for them and adds them in slice order before its
+        // thread at the same position reads them back; lane-interleaved 16-byte granules), slice 0 waits for them and adds them in slice order before its
         // epilogue -- a fixed summation order, so the result does not depend on timing.
         const int tail_idx = tile - g.full_tiles;
         constexpr int kWarpWs = kChunks * 1024;   // floats per warp and partial tile
@@ -636,7 +636,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t(&r)[32] = acc[ch & 1];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              *reinterpret_cast<uint4*>(wsp + ch * 1024 + lane * 32 + 4 * k) =
+              *reinterpret_cast<uint4*>(wsp + ((ch * 8 + k) * 32 + lane) * 4) =   // lane-interleaved: 512 B per request
                   make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
           }
           __threadfence();
@@ -673,10 +673,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int sl = 1; sl < g.tail_split; ++sl) {
               const float* wsp = g.splitk_ws +
                                  ((((size_t)tail_idx * (g.tail_split - 1) + (sl - 1)) * CG + cta_rank) * 8 + warp) * kWarpWs +
-                                 ch * 1024 + lane * 32;
+                                 ch * 1024 + lane * 4;
+              float4 pvs[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) pvs[k] = __ldcg(reinterpret_cast<const float4*>(wsp + k * 128));
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                const float4 pv = __ldcg(reinterpret_cast<const float4*>(wsp + 4 * k));
+                const float4 pv = pvs[k];
                 uint32_t(&ra)[32] = acc[ch & 1];
                 ra[4 * k] = __float_as_uint(__uint_as_float(ra[4 * k]) + pv.x);
                 ra[4 * k + 1] = __float_as_uint(__uint_as_float(ra[4 * k + 1]) + pv.y);
@@ -848,6 +851,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
+// maximum number of K slices per tail tile (0 / 1 = no split); VQ_GEMM_TAIL_SPLIT or vq_gemm_tune.
+// OFF by default -- measured on B200 (round 2, scripts/gemm_split_ab.py): the partially filled last round of the static
+// schedule costs far less than a full round (the few busy CTA pairs run with less L2 / HBM contention and higher
+// clocks under the power cap): splitting the tail mainloop 3 ways WITHOUT any fix-up leaves fc2 at M = 10 992
+// unchanged (82.6 vs 82.2 us), and the fix-up adds 7-13 us.  The path stays as a tested, deterministic option.
+static int g_gemm_tail_split = [] {
+  const char* e = getenv("VQ_GEMM_TAIL_SPLIT");
+  const int v = e ? atoi(e) : 0;
+  return v < 0 ? 0 : v > 8 ? 8 : v;
+}();
+
 template <int BLOCK_N, int MODE, bool OUT_F32, int CG>
 static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
@@ -856,23 +870,20 @@ static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmAr
   const int sms = num_sms();
   const int units = CG == 2 ? sms / 2 : sms;                     // CTAs (pairs) of a persistent grid
   int grid_units = g.total_tiles < units ? g.total_tiles : units;
-  // Wave quantisation: the last round of a static round-robin schedule runs R = tiles mod units tiles on `units`
-  // CTAs (pairs).  When R leaves at least half of them idle, every tail tile is split along K into floor(units / R)
-  // slices (<= 4, >= 4 k-blocks each) that different CTAs work on concurrently; slice 0 adds the partial accumulators
-  // of the others in slice order (deterministic) before its epilogue.  c2 fc2: 172 tiles on 74 pairs = 3 rounds -> 2.33.
+  // Optional (see g_gemm_tail_split): the last round of a static round-robin schedule runs R = tiles mod units tiles
+  // on `units` CTAs (pairs).  When R leaves at least half of them idle, every tail tile can be split along K into
+  // floor(units / R) slices (>= 4 k-blocks each) that different CTAs work on concurrently; slice 0 adds the partial
+  // accumulators of the others in slice order (deterministic) before its epilogue.
   g.full_tiles = g.total_tiles / units * units;
   g.tail_split = 1;
   g.splitk_ws = nullptr;
   g.splitk_flags = nullptr;
   const int n_tail = g.total_tiles - g.full_tiles;
-  static const int split_on = [] {
-    const char* e = getenv("VQ_GEMM_TAIL_SPLIT");
-    return e ? atoi(e) : 1;
-  }();
+  const int split_on = g_gemm_tail_split;
   if (MODE != VQ_EPI_QKV_ROPE && split_on && n_tail > 0 && g.total_tiles == g.m_tiles * g.n_tiles) {
     const int num_kb = (g.K + kBlockK - 1) / kBlockK;
     int split = units / n_tail;
-    if (split > 4) split = 4;
+    if (split > split_on) split = split_on;
     while (split > 1 && num_kb / split < 4) --split;
     constexpr size_t kTileWsFloats = (size_t)CG * 8 * (BLOCK_N / 2 / 32) * 1024;
     const size_t need = (size_t)n_tail * (split - 1) * kTileWsFloats * sizeof(float);
@@ -923,6 +934,11 @@ static int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs&
 static inline bool fits_i32(long long v) { return v >= INT32_MIN && v <= INT32_MAX; }
 
 }  // namespace vq
+
+extern "C" int vq_gemm_tune(int32_t tail_split_max) {
+  if (tail_split_max >= 0) vq::g_gemm_tail_split = tail_split_max > 8 ? 8 : tail_split_max;
+  return VQ_OK;
+}
 
 extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
   using namespace vq;

@@ -95,6 +95,11 @@ def gemm(
     return out
 
 
+def gemm_tune(tail_split_max: int = -1) -> None:
+    """Maximum K slices per tail tile of the persistent GEMM schedule (0 / 1 = no split); -1 keeps the setting."""
+    _lib.check(_lib.lib().vq_gemm_tune(tail_split_max), "vq_gemm_tune")
+
+
 def gemm_desc(**kw) -> None:
     """Launch a GEMM from explicit descriptor fields (batched / strided use)."""
     d = GemmDesc()
