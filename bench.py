@@ -16,9 +16,9 @@ Workloads (BASELINE.json `configs`, synthetic 518x518 inputs, random-init weight
   The default N = 1 line also carries c3 and c4 (`workloads`), measured the same way with fewer steps.
 
 One JSON line is printed by rank 0.  `value` = frames/s with inputs resident in HBM; `e2e` = the same step through the
-public API from pinned HOST memory: uint8 views -> H2D (double-buffered on a copy stream) -> ops.preprocess_views ->
-VGGTQwen3VLM.encode_image_tokens + project_tokens + backward + optimizer (c2) / encode_images (c3, c4) -> D2H of the
-projected tokens, every step.  `roofline` = the dominant kernel's algorithmic FLOPs / its CUDA-event launch time
+public API from pinned HOST memory: uint8 views -> H2D (double-buffered on a copy stream) -> VGGTQwen3VLM.prepare_views
+(a no-op for views that already are 518 px: the patch kernel consumes the bytes) -> encode_image_tokens + project_tokens
++ backward + optimizer (c2) / encode_images (c3, c4) -> D2H of the projected tokens, every step.  `roofline` = the dominant kernel's algorithmic FLOPs / its CUDA-event launch time
 against MEASURED_PEAKS.json, with the DRAM traffic of the committed ncu capture (profiles/ncu_traffic.json).
 Baselines on the same box (N = 1 only; reported, not targets): `cpu_baseline` = the reference path in fp32 PyTorch on
 the host cores; `gpu_eager_bf16` = the same PyTorch modules in bf16 on the B200 (cuBLAS + SDPA flash + ATen), the
@@ -252,7 +252,7 @@ def run_b200(args) -> dict:
         model.train(train)
         gen = torch.Generator().manual_seed(1234 + rank)
         views_host = torch.randint(0, 256, (B, S, 518, 518, 3), generator=gen, dtype=torch.uint8).pin_memory()
-        images_dev = ops.preprocess_views(views_host.to(dev), 518)       # f32 [B,S,3,518,518] in [0,1], resident
+        images_dev = model.prepare_views(views_host.to(dev), 518)        # 518-px views: stay uint8, resident in HBM
         grad_out = torch.randn(B, NUM_VIS_TOKENS, TEXT_HIDDEN, generator=gen).to(dev) if bwd else None
         result_host = torch.empty(B, NUM_VIS_TOKENS, TEXT_HIDDEN, dtype=torch.float32).pin_memory()
         if bwd and optimizer is None:
@@ -294,7 +294,7 @@ def run_b200(args) -> dict:
                 state["primed"] = True
             torch.cuda.current_stream().wait_event(ready[slot])              # this step's views have landed
             h2d(slot ^ 1)                                                    # H2D of the next step's views
-            images = ops.preprocess_views(bufs[slot], 518)                   # uint8 HWC -> f32 CHW in [0,1] on the GPU
+            images = model.prepare_views(bufs[slot], 518)                    # resize / crop only if the size differs
             if bwd:
                 out = train_tail(model.encode_image_tokens(images))
             else:
@@ -376,8 +376,8 @@ def run_b200(args) -> dict:
         "e2e": {"value": round(frames / (main["ms_e2e"] / 1e3), 2), "unit": "frames/s",
                 "ms_per_step": round(main["ms_e2e"], 3), "h2d_bytes_per_step": main["h2d"],
                 "d2h_bytes_per_step": main["d2h"],
-                "api": ("ops.preprocess_views + VGGTQwen3VLM.encode_image_tokens + project_tokens (= encode_images_trainable)"
-                        " + backward + ShardedAdamW.step" if bwd else "ops.preprocess_views + VGGTQwen3VLM.encode_images") +
+                "api": ("VGGTQwen3VLM.prepare_views + encode_image_tokens + project_tokens (= encode_images_trainable)"
+                        " + backward + ShardedAdamW.step" if bwd else "VGGTQwen3VLM.prepare_views + encode_images") +
                        "; uint8 views H2D double-buffered on a copy stream, projected tokens read back every step"},
         "gpu_launches": int(main["launches"]) * args.steps,
         "gpu_launches_per_step": int(main["launches"]),

@@ -191,6 +191,11 @@ int vq_attention_tune_bounded(int32_t enable, int32_t emu_pairs);
  * -> bf16 [frames*gh*gw, Kp], column = c*patch^2 + dy*patch + dx, zero padded to Kp (multiple of 8). */
 int vq_im2col_patches(const float* images, void* out_bf16, int32_t frames, int32_t H, int32_t W, int32_t patch,
                       int32_t Kp, vq_stream_t stream);
+/* The same from uint8 views [frames, H, W, 3] (what the image decoder / the H2D copy delivers): ToTensor's x / 255
+ * (src/dataio/collate_multiview.py:17) is applied inside, bit-identical to the f32 path, and the f32 image is never
+ * materialised. */
+int vq_im2col_patches_u8(const uint8_t* views_hwc, void* out_bf16, int32_t frames, int32_t H, int32_t W, int32_t patch,
+                         int32_t Kp, vq_stream_t stream);
 
 /* K3: DINOv2 token assembly ([UPSTREAM] DinoVisionTransformer.prepare_tokens_with_masks): row 0 of every frame =
  * cls_token + pos_embed[0]; rows 1..n_special-1 = register_tokens (no positional embedding). x is f32 [frames*P, D]. */
@@ -351,16 +356,17 @@ typedef struct vq_aggregator_cfg {
   int32_t n_special;   /* patch_start_idx = 1 + registers = 5 */
   int32_t Kp;          /* padded im2col width (592) */
   float stem_eps, block_eps, qk_eps; /* 1e-6, 1e-5, 1e-5 */
+  int32_t images_u8;   /* 0: images are f32 [B,S,3,H,W] in [0,1];  1: uint8 views [B,S,H,W,3] (x / 255 applied inside) */
 } vq_aggregator_cfg;
 
 size_t vq_aggregator_workspace_bytes(const vq_aggregator_cfg* cfg);
 
-/* images: f32 [B,S,3,H,W] in [0,1].
+/* images: f32 [B,S,3,H,W] in [0,1], or uint8 [B,S,H,W,3] when cfg->images_u8.
  * out_tokens: bf16 [B, n_take, 2D] = cat(frame_out, global_out)[-1] flattened over views, first n_take tokens
  *             (n_take = num_vis_tokens for encode_images; S*P for the full last list entry).
  * out_all: NULL, or `depth` device pointers, each bf16 [B, S*P, 2D], receiving every iteration's concat
  *          (the full list the upstream call returns; the reference only reads [-1]). */
-int vq_aggregator_forward(const vq_aggregator_cfg* cfg, const vq_aggregator_weights* w, const float* images,
+int vq_aggregator_forward(const vq_aggregator_cfg* cfg, const vq_aggregator_weights* w, const void* images,
                           void* out_tokens, int32_t n_take, void* const* out_all, void* workspace,
                           size_t workspace_bytes, vq_stream_t stream);
 

@@ -69,3 +69,24 @@ def test_layernorm_folding_matches_the_two_kernel_form():
         assert_token_parity(outs[fold], ref_list[-1], f"fold_layernorm={fold}")
     assert outs[(True, "launches")] < outs[(False, "launches")]
     assert_token_parity(outs[True], outs[False].float(), "folded vs two-kernel form", cos_min=0.9995, rel_max=1.5e-2)
+
+
+def test_uint8_views_equal_the_float_path_bit_for_bit():
+    """uint8 views [B,S,H,W,3] straight into the patch kernel (x / 255 + normalise + im2col fused, 16-byte stores)
+    give the same tokens, bit for bit, as ToTensor's float image through the f32 path."""
+    cfg = AggregatorConfig(img_size=126, embed_dim=256, num_heads=4, depth=2, stem_depth=2)
+    state = init_aggregator_state(cfg, seed=0, sensitised=True)
+    agg = _build(cfg, state)
+    views = torch.randint(0, 256, (2, 3, 126, 126, 3), generator=torch.Generator().manual_seed(4), dtype=torch.uint8)
+    as_float = views.permute(0, 1, 4, 2, 3).float().div(255)          # torchvision ToTensor
+    a = agg.encode_tokens(views.cuda(), None)
+    b = agg.encode_tokens(as_float.cuda(), None)
+    assert torch.equal(a, b)
+    ref_list, _ = aggregator_forward(state, as_float, cfg, return_all=False)
+    assert_token_parity(a.view(2, 3, -1, 512), ref_list[-1], "uint8 views")
+    # odd base alignment of the byte strip (a view into a larger buffer)
+    big = torch.zeros(views.numel() + 7, dtype=torch.uint8, device="cuda")
+    for off in (1, 2, 3):
+        v = big[off:off + views.numel()].view(views.shape)
+        v.copy_(views)
+        assert torch.equal(agg.encode_tokens(v, None), b)

@@ -248,11 +248,15 @@ class Aggregator(nn.Module):
         """images [B,S,3,H,W] in [0,1] -> bf16 [B, n_take, 2D]: the first n_take tokens of the view-flattened last
         aggregator output (what encode_images keeps).  With return_all, also the list of every iteration's
         [B,S,P,2D] output."""
-        if images.dim() != 5 or images.shape[2] != 3:
-            raise ValueError(f"expected images [B,S,3,H,W], got {tuple(images.shape)}")
+        u8 = images.dtype == torch.uint8
+        if images.dim() != 5 or images.shape[4 if u8 else 2] != 3:
+            raise ValueError(f"expected float images [B,S,3,H,W] or uint8 views [B,S,H,W,3], got {tuple(images.shape)}")
         if not images.is_cuda:
             raise RuntimeError("Aggregator runs on sm_100a only: images must be a CUDA tensor (no CPU fallback)")
-        B, S, _, H, W = images.shape
+        if u8:      # views as decoded (HWC bytes): x / 255 happens inside the patch kernel, no f32 image is built
+            B, S, H, W, _ = images.shape
+        else:
+            B, S, _, H, W = images.shape
         ps = self.patch_size
         if H % ps or W % ps:
             raise ValueError(f"image size {(H, W)} must be a multiple of the patch size {ps}")
@@ -260,9 +264,10 @@ class Aggregator(nn.Module):
         P = self.patch_start_idx + gh * gw
         n_take = S * P if n_take is None else min(int(n_take), S * P)
         dev = images.device
-        img = images.detach().to(torch.float32).contiguous()
+        img = images.detach().contiguous() if u8 else images.detach().to(torch.float32).contiguous()
         packed = self._pack(dev, gh, gw)
         cfg = self._cfg(B, S, H, W)
+        cfg.images_u8 = 1 if u8 else 0
         ws = self._workspace(cfg, dev)
         base = (ws.data_ptr() + 1023) // 1024 * 1024
         out = torch.empty(B, n_take, 2 * self.embed_dim, dtype=torch.bfloat16, device=dev)
@@ -284,7 +289,7 @@ class Aggregator(nn.Module):
         """Upstream signature: (aggregated_tokens_list, patch_start_idx).  By default the list holds only the last
         iteration's [B,S,P,2D] tensor — the only entry the reference reads (src/models/vggt_qwen3_vlm.py:148) —
         so 23 dead 5.6 MB/frame concats are skipped; `return_all=True` materialises all `depth` entries."""
-        B, S = images.shape[:2]
+        B, S = images.shape[:2]   # float [B,S,3,H,W] or uint8 [B,S,H,W,3]
         if return_all:
             _, outs = self.encode_tokens(images, None, return_all=True)
             return outs, self.patch_start_idx

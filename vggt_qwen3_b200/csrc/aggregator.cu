@@ -167,7 +167,7 @@ extern "C" size_t vq_aggregator_workspace_bytes(const vq_aggregator_cfg* cfg) {
 }
 
 extern "C" int vq_aggregator_forward(const vq_aggregator_cfg* c, const vq_aggregator_weights* w,
-                                     const float* images, void* out_tokens, int32_t n_take,
+                                     const void* images, void* out_tokens, int32_t n_take,
                                      void* const* out_all, void* workspace, size_t workspace_bytes,
                                      vq_stream_t stream) {
   int rc = check_cfg(c);
@@ -189,7 +189,8 @@ extern "C" int vq_aggregator_forward(const vq_aggregator_cfg* c, const vq_aggreg
   VQ_CHECK_ARG(workspace_bytes >= ws.total, "workspace too small");
 
   // ---- DINOv2 stem: normalise + im2col -> patch-embed GEMM (+bias +pos_embed) -> special rows
-  rc = vq_im2col_patches(images, ws.h, F, c->H, c->W, c->patch, c->Kp, stream);
+  rc = c->images_u8 ? vq_im2col_patches_u8(reinterpret_cast<const uint8_t*>(images), ws.h, F, c->H, c->W, c->patch, c->Kp, stream)
+                    : vq_im2col_patches(reinterpret_cast<const float*>(images), ws.h, F, c->H, c->W, c->patch, c->Kp, stream);
   if (rc) return rc;
   {
     vq_gemm_desc g;

@@ -113,10 +113,9 @@ struct GemmCfg {
   static_assert(kStages >= 3, "smem ring too shallow");
 };
 
-// ---- GELU (exact erf form) without erff(): Phi(x) = 0.5 (1 + E(t)), t = clamp(x, -4.2, 4.2), E(t) = t P(t^2) with P a
-// degree-8 minimax polynomial constrained to E(4.2) = 1 (so gelu(x) = x for x >= 4.2 and 0 for x <= -4.2).
-// Max abs error of gelu against the erf definition: 5.9e-5 (bf16 rounding of the result is 2e-3 relative).
-// Evaluated two columns at a time with packed fp32 FMAs (FFMA2).
+// ---- erf without erff() (used by the GELU derivative): Phi(x) = 0.5 (1 + E(t)), t = clamp(x, -4.2, 4.2), E(t) = t P(t^2)
+// with P a degree-8 minimax polynomial constrained to E(4.2) = 1.  Max abs error of x Phi(x) against the erf
+// definition: 5.9e-5.  Evaluated two columns at a time with packed fp32 FMAs (FFMA2).
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;
   asm("{.reg .b64 ra, rb, rc, rd;\n"
@@ -149,12 +148,30 @@ __device__ __forceinline__ float2 erf_sqrt2_poly2(float2 t) {
   p = ffma2(p, u, splat2(7.976739407e-01f));
   return ffma2(p, t, splat2(0.f));
 }
+// Forward GELU (exact erf form) through the complementary normal CDF, whose logarithm is nearly polynomial:
+//   gelu(x) = x Phi(x) = max(x, 0) - |x| Q(|x|),   Q(a) = 1 - Phi(a) = 0.5 erfc(a / sqrt(2)) ~= 2^p(a),
+//   p(a) = -1 + a (c1 + a (c2 + a (c3 + a c4)))   (minimax fit of a Q(a) on [0, 9], p(0) = -1 exactly so that the slope at
+//   the origin is exact).  Max abs error of gelu against the erf definition: 1.3e-5 (bf16 rounding of the result is 2e-3
+//   relative).  4 FMAs + one MUFU.EX2 + 3 cheap ops per element instead of a degree-8 polynomial: the epilogue of the
+//   K = 1024 fc1 GEMM is issue-bound, every instruction per element shows up in its run time.
+__device__ __forceinline__ float gelu1(float x) {
+  const float a = fminf(fabsf(x), 8.0f);        // 2^p(8) = 2^-47: the correction has vanished long before
+  float p = fmaf(a, 0.0038706841245f, -0.044546267023f);
+  p = fmaf(a, p, -0.46639128587f);
+  p = fmaf(a, p, -1.14905086599f);
+  p = fmaf(a, p, -1.0f);
+  return fmaf(-fabsf(x), ex2_approx(p), fmaxf(x, 0.f));
+}
+#ifdef VQ_GELU_POLY   // A/B builds: the degree-8 erf polynomial form
 __device__ __forceinline__ float2 gelu2(float2 x) {
   const float2 t = make_float2(clamp_sym(x.x, 4.2f), clamp_sym(x.y, 4.2f));
   const float2 e = erf_sqrt2_poly2(t);
   const float2 hx = ffma2(x, splat2(0.5f), splat2(0.f));
   return ffma2(hx, e, hx);
 }
+#else
+__device__ __forceinline__ float2 gelu2(float2 x) { return make_float2(gelu1(x.x), gelu1(x.y)); }
+#endif
 // gelu'(x) = Phi(x) + x phi(x)
 __device__ __forceinline__ float2 gelu_grad2(float2 x) {
   const float2 t = make_float2(clamp_sym(x.x, 4.2f), clamp_sym(x.y, 4.2f));

@@ -19,39 +19,73 @@ __device__ __forceinline__ int warp_max_i(int v) {
 
 // ------------------------------------------------------------------------------------------------
 // K1 + K2 front: (x - mean) / std, then im2col of 14x14/14 patches into bf16 rows [c*ps*ps + dy*ps + dx].
-// One CTA per (frame, patch row): the 3 x ps x W strip is read coalesced, staged in smem as bf16,
-// and written out one patch row (Kp bf16) at a time.
+// One CTA per (frame, patch row): the 3 x ps x W strip is read coalesced, staged in smem as normalised bf16
+// ([c][dy][x]), and written out as whole patch rows with 16-byte stores (8 consecutive k per thread).
+// SRC_U8 = false: f32 images [frames, 3, H, W] in [0, 1];  SRC_U8 = true: uint8 views [frames, H, W, 3] straight from the
+// decoder / H2D copy -- ToTensor's x / 255 is applied here, bit-identical to torchvision (IEEE division), so the f32
+// image is never materialised (4x less input traffic: 3.22 MB -> 0.80 MB per frame).
 // ------------------------------------------------------------------------------------------------
+template <bool SRC_U8>
 __global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W, int ps,
-              int gh, int gw, int Kp) {
+im2col_kernel(const void* __restrict__ src, __nv_bfloat16* __restrict__ out, int H, int W, int ps, int gh, int gw,
+              int Kp) {
   extern __shared__ __nv_bfloat16 strip[];  // [3][ps][Wc], Wc = gw*ps
   const int f = blockIdx.x / gh, gy = blockIdx.x % gh;
   const int Wc = gw * ps;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float istd[3] = {1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f};
-  const int n = 3 * ps * Wc;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int x = i % Wc;
-    const int dy = (i / Wc) % ps;
-    const int c = i / (Wc * ps);
-    const float v = img[(((long long)f * 3 + c) * H + gy * ps + dy) * W + x];
-    strip[i] = __float2bfloat16((v - mean[c]) * istd[c]);
+  if constexpr (SRC_U8) {
+    // the ps rows of the strip are one contiguous run of ps * W * 3 bytes in HWC order: read it as 32-bit words where
+    // the alignment allows, scatter the bytes into the [c][dy][x] layout
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(src) + ((size_t)f * H + (size_t)gy * ps) * W * 3;
+    const int nbytes = ps * W * 3;
+    const int lead = (int)((4 - (reinterpret_cast<uintptr_t>(base) & 3)) & 3);   // bytes before the first aligned word
+    auto put = [&](int byte_index, unsigned v) {
+      const int pix = byte_index / 3, c = byte_index - pix * 3;
+      const int dy = pix / W, x = pix - dy * W;
+      if (x < Wc) strip[(c * ps + dy) * Wc + x] = __float2bfloat16(((float)v / 255.0f - mean[c]) * istd[c]);
+    };
+    for (int i = threadIdx.x; i < lead && i < nbytes; i += blockDim.x) put(i, base[i]);
+    const int nwords = (nbytes - lead) / 4;
+    const unsigned* words = reinterpret_cast<const unsigned*>(base + lead);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+      const unsigned w = __ldg(words + i);
+      const int b0 = lead + 4 * i;
+      put(b0, w & 0xFFu); put(b0 + 1, (w >> 8) & 0xFFu); put(b0 + 2, (w >> 16) & 0xFFu); put(b0 + 3, w >> 24);
+    }
+    for (int i = lead + 4 * nwords + threadIdx.x; i < nbytes; i += blockDim.x) put(i, base[i]);
+  } else {
+    const float* img = reinterpret_cast<const float*>(src);
+    const int n = 3 * ps * Wc;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int x = i % Wc;
+      const int dy = (i / Wc) % ps;
+      const int c = i / (Wc * ps);
+      const float v = img[(((long long)f * 3 + c) * H + gy * ps + dy) * W + x];
+      strip[i] = __float2bfloat16((v - mean[c]) * istd[c]);
+    }
   }
   __syncthreads();
   const int K = 3 * ps * ps;
-  const int total = gw * Kp;
+  const int k8 = Kp / 8;                       // 16-byte granules per patch row
+  const int total = gw * k8;
   __nv_bfloat16* dst = out + ((long long)f * gh + gy) * gw * Kp;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int gx = i / Kp, k = i - gx * Kp;
-    __nv_bfloat16 v = __float2bfloat16(0.f);
-    if (k < K) {
-      const int c = k / (ps * ps);
-      const int r = k - c * ps * ps;
-      const int dy = r / ps, dx = r - dy * ps;
-      v = strip[(c * ps + dy) * Wc + gx * ps + dx];
+    const int gx = i / k8, k0 = (i - gx * k8) * 8;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      __nv_bfloat16 e = __float2bfloat16(0.f);
+      if (k < K) {
+        const int c = k / (ps * ps);
+        const int r = k - c * ps * ps;
+        const int dy = r / ps, dx = r - dy * ps;
+        e = strip[(c * ps + dy) * Wc + gx * ps + dx];
+      }
+      v[j] = e;
     }
-    dst[i] = v;
+    *reinterpret_cast<uint4*>(dst + (long long)gx * Kp + k0) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -263,21 +297,34 @@ splice_overwrite_kernel(T* __restrict__ embeds, const long long* __restrict__ id
 // ==================================================================================================
 using namespace vq;
 
-extern "C" int vq_im2col_patches(const float* images, void* out_bf16, int32_t frames, int32_t H, int32_t W,
-                                 int32_t patch, int32_t Kp, vq_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int im2col_launch(const void* images, bool u8, void* out_bf16, int32_t frames, int32_t H, int32_t W, int32_t patch,
+                         int32_t Kp, cudaStream_t stream) {
   VQ_CHECK_ARG(images && out_bf16, "null pointer");
   VQ_CHECK_ARG(frames > 0 && patch > 0 && H >= patch && W >= patch, "image geometry");
   const int gh = H / patch, gw = W / patch;
   VQ_CHECK_ARG(Kp >= 3 * patch * patch && Kp % 8 == 0, "Kp must be >= 3*patch^2 and a multiple of 8");
+  VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(out_bf16) % 16) == 0, "patch matrix must be 16-byte aligned");
   const size_t smem = (size_t)3 * patch * gw * patch * sizeof(__nv_bfloat16);
   VQ_CHECK_ARG(smem <= 200 * 1024, "image too wide for the im2col strip");
-  if (smem > 48 * 1024) VQ_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(im2col_kernel), (int)smem));
-  LaunchScope scope(kKindRow, "im2col", frames, H, W, 0, (double)frames * (3.0 * H * W * 4 + (double)gh * gw * Kp * 2), stream);
-  im2col_kernel<<<frames * gh, 256, smem, stream>>>(images, reinterpret_cast<__nv_bfloat16*>(out_bf16), H, W, patch,
-                                                    gh, gw, Kp);
+  const void* kern = u8 ? reinterpret_cast<const void*>(im2col_kernel<true>) : reinterpret_cast<const void*>(im2col_kernel<false>);
+  if (smem > 48 * 1024) VQ_CHECK_CUDA(ensure_dynamic_smem(kern, (int)smem));
+  LaunchScope scope(kKindRow, u8 ? "im2col_u8" : "im2col", frames, H, W, 0,
+                    (double)frames * (3.0 * H * W * (u8 ? 1 : 4) + (double)gh * gw * Kp * 2), stream);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (u8) im2col_kernel<true><<<frames * gh, 256, smem, stream>>>(images, out, H, W, patch, gh, gw, Kp);
+  else im2col_kernel<false><<<frames * gh, 256, smem, stream>>>(images, out, H, W, patch, gh, gw, Kp);
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
+}
+
+extern "C" int vq_im2col_patches(const float* images, void* out_bf16, int32_t frames, int32_t H, int32_t W,
+                                 int32_t patch, int32_t Kp, vq_stream_t stream_) {
+  return im2col_launch(images, false, out_bf16, frames, H, W, patch, Kp, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vq_im2col_patches_u8(const uint8_t* views_hwc, void* out_bf16, int32_t frames, int32_t H, int32_t W,
+                                    int32_t patch, int32_t Kp, vq_stream_t stream_) {
+  return im2col_launch(views_hwc, true, out_bf16, frames, H, W, patch, Kp, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int vq_init_special_tokens(float* x, const float* cls_token, const float* pos_embed0,

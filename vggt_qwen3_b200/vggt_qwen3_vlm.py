@@ -102,11 +102,26 @@ class VGGTQwen3VLM(nn.Module):
         return model
 
     # ------------------------------------------------------------------ hot path
+    @staticmethod
+    def prepare_views(views_u8: torch.Tensor, image_size: int) -> torch.Tensor:
+        """The reference's per-view transform (src/dataio/collate_multiview.py:12-19: Resize(image_size, BICUBIC) +
+        CenterCrop + ToTensor) on the GPU, for uint8 views [B, V, H, W, 3] as decoded: views that already have the
+        target size are passed through as uint8 (the patch kernel applies x / 255 itself, nothing is materialised);
+        others are resized / cropped bit-exactly (ops.preprocess_views) to float [B, V, 3, image_size, image_size]."""
+        if views_u8.dtype != torch.uint8 or views_u8.dim() != 5 or views_u8.shape[-1] != 3:
+            raise ValueError("prepare_views expects uint8 views [B, V, H, W, 3]")
+        if views_u8.shape[2] == image_size and views_u8.shape[3] == image_size:
+            return views_u8
+        return ops.preprocess_views(views_u8, image_size)
+
     def _vision_tokens(self, images: torch.Tensor) -> torch.Tensor:
-        """[B, num_vis_tokens, embed_dim]: first tokens of the view-flattened last aggregator iteration (:144-156)."""
+        """[B, num_vis_tokens, embed_dim]: first tokens of the view-flattened last aggregator iteration (:144-156).
+        `images`: float [B,V,3,H,W] in [0,1] like the reference, or uint8 views [B,V,H,W,3] (see prepare_views)."""
         agg_mod = self.vision_model.aggregator
         if isinstance(agg_mod, Aggregator):
             return agg_mod.encode_tokens(images, self.num_vis_tokens)
+        if images.dtype == torch.uint8:
+            images = images.permute(0, 1, 4, 2, 3).float() / 255.0
         tokens_list, _ = agg_mod(images.to(dtype=torch.bfloat16))
         agg = tokens_list[-1]
         if agg.dim() == 4:
