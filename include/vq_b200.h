@@ -208,6 +208,12 @@ int vq_layernorm(const void* in, int32_t in_dtype, void* out, int32_t out_dtype,
                  const float* beta, int64_t rows, int32_t D, float eps, float* mean_out, float* rstd_out,
                  vq_stream_t stream);
 
+/* Residual add fused with the LayerNorm after it ([UPSTREAM] Block.forward: x = x + ls(branch(norm(x)))): x (f32 [rows, D],
+ * in place) += y (bf16 [rows, D]: the LayerScale-d branch output written by the proj / fc2 GEMM), then
+ * xn = LayerNorm(x) (bf16) for the GEMM that follows; xn == NULL: the add only (last block of a chain). */
+int vq_residual_layernorm(float* x, const void* y_bf16, void* xn_bf16, const float* gamma, const float* beta, int64_t rows,
+                          int32_t D, float eps, vq_stream_t stream);
+
 /* Entry of a LayerNorm-folded block chain: stats[m] = (sum, sum of squares) of row m of x (f32 [rows, D]), xb = bf16(x),
  * stats_zero (optional, 2*rows floats) cleared: what the proj / fc2 epilogues maintain from then on. */
 int vq_row_stats_cast(const float* x, void* xb_bf16, float* stats, float* stats_zero, int64_t rows, int32_t D,
@@ -356,6 +362,10 @@ typedef struct vq_aggregator_cfg {
   int32_t n_special;   /* patch_start_idx = 1 + registers = 5 */
   int32_t Kp;          /* padded im2col width (592) */
   float stem_eps, block_eps, qk_eps; /* 1e-6, 1e-5, 1e-5 */
+  /* 1 (recommended): the residual adds are deferred into the LayerNorm pass that follows them (proj / fc2 write a bf16
+   * branch output, one row kernel does x += y and the next LayerNorm); 0: f32 read-modify-write in the GEMM epilogues
+   * + standalone LayerNorm launches.  Ignored when the weights are LayerNorm-folded. */
+  int32_t deferred_residual;
   int32_t images_u8;   /* 0: images are f32 [B,S,3,H,W] in [0,1];  1: uint8 views [B,S,H,W,3] (x / 255 applied inside) */
 } vq_aggregator_cfg;
 

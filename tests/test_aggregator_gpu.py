@@ -71,6 +71,25 @@ def test_layernorm_folding_matches_the_two_kernel_form():
     assert_token_parity(outs[True], outs[False].float(), "folded vs two-kernel form", cos_min=0.9995, rel_max=1.5e-2)
 
 
+def test_block_schedules_agree():
+    """Default schedule (residual add deferred into the following LayerNorm pass, bf16 branch outputs) against the
+    round-1 schedule (f32 read-modify-write in the GEMM epilogues): same tokens up to bf16 rounding of the branch
+    outputs, both within the parity tolerance of the oracle; sensitised weights (LayerScale up to 1)."""
+    cfg = AggregatorConfig(img_size=126, embed_dim=256, num_heads=4, depth=3, stem_depth=2)
+    state = init_aggregator_state(cfg, seed=0, sensitised=True)
+    images = torch.rand(2, 2, 3, 126, 126, generator=torch.Generator().manual_seed(1))
+    ref_list, _ = aggregator_forward(state, images, cfg, return_all=True)
+    agg = _build(cfg, state)
+    outs = {}
+    for deferred in (True, False):
+        agg.deferred_residual = deferred
+        lst, _ = agg(images.cuda(), return_all=True)
+        for i, (o, r) in enumerate(zip(lst, ref_list)):
+            assert_token_parity(o, r, f"deferred_residual={deferred} iteration {i}")
+        outs[deferred] = lst[-1]
+    assert_token_parity(outs[True], outs[False].float(), "deferred vs epilogue residual", cos_min=0.9995, rel_max=1.5e-2)
+
+
 def test_uint8_views_equal_the_float_path_bit_for_bit():
     """uint8 views [B,S,H,W,3] straight into the patch kernel (x / 255 + normalise + im2col fused, 16-byte stores)
     give the same tokens, bit for bit, as ToTensor's float image through the f32 path."""

@@ -92,7 +92,7 @@ class AggregatorCfg(C.Structure):
         ("D", C.c_int32), ("heads", C.c_int32), ("hidden", C.c_int32),
         ("n_special", C.c_int32), ("Kp", C.c_int32),
         ("stem_eps", C.c_float), ("block_eps", C.c_float), ("qk_eps", C.c_float),
-        ("images_u8", C.c_int32),
+        ("deferred_residual", C.c_int32), ("images_u8", C.c_int32),
     ]
 
 
@@ -192,6 +192,7 @@ _EXTRA_DECLS: dict[str, list] = {
     "vq_im2col_patches_u8": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "vq_init_special_tokens": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "vq_layernorm": [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp],
+    "vq_residual_layernorm": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp],
     "vq_row_stats_cast": [_vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "vq_stem_finalize": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
     "vq_gather_tokens": [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp],

@@ -121,6 +121,10 @@ class Aggregator(nn.Module):
         # atomics of the row statistics make the result run-to-run non-bit-identical.  VQ_FOLD_LN=1 or
         # `fold_layernorm = True` + invalidate_packed() selects it (parity-tested both ways).
         self.fold_layernorm = os.environ.get("VQ_FOLD_LN", "0") == "1"
+        # Default schedule: residual adds deferred into the LayerNorm pass after them (vq_residual_layernorm); the proj /
+        # fc2 GEMMs then write a bf16 branch output with a plain epilogue.  VQ_DEFERRED_RESIDUAL=0 = round-1 schedule
+        # (f32 read-modify-write in the GEMM epilogue + standalone LayerNorm).
+        self.deferred_residual = os.environ.get("VQ_DEFERRED_RESIDUAL", "1") != "0"
         self._packed: Optional[dict] = None
         self._workspaces: Dict[tuple, torch.Tensor] = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
@@ -230,6 +234,7 @@ class Aggregator(nn.Module):
         c.D, c.heads, c.hidden = self.embed_dim, self.num_heads, self.hidden
         c.n_special, c.Kp = self.patch_start_idx, self.Kp
         c.stem_eps, c.block_eps, c.qk_eps = 1e-6, 1e-5, 1e-5
+        c.deferred_residual = 1 if self.deferred_residual else 0
         return c
 
     def _workspace(self, cfg: AggregatorCfg, device: torch.device) -> torch.Tensor:

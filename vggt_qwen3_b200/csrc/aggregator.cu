@@ -8,6 +8,7 @@
 //   qkv   bf16 [M, 3D]      q | k | v column blocks, q/k normalised + rotated, q pre-scaled
 //   att   bf16 [M, D]       attention output
 //   h     bf16 [M, hidden]  GELU(fc1) (the im2col patch matrix aliases this buffer before block 0)
+//   y     bf16 [M, D]       LayerScale-d branch output of proj / fc2 (deferred-residual schedule)
 // Frame attention views the rows as B*S sequences of P tokens, global attention as B sequences of
 // S*P tokens; the buffer is never permuted.
 #include <math.h>
@@ -21,7 +22,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
   float* x;
-  void *xn, *qkv, *att, *h;
+  void *xn, *qkv, *att, *h, *y;
   float* stats[2];   // LayerNorm-folded chain: (sum, sum of squares) per row, two buffers that ping-pong
   size_t total;
 };
@@ -45,6 +46,7 @@ Workspace carve(const vq_aggregator_cfg* c, void* base) {
   const size_t patch_bytes = (size_t)c->B * c->S * gh * gw * c->Kp * 2;
   const size_t o_h = take(h_bytes > patch_bytes ? h_bytes : patch_bytes);
   const size_t o_s0 = take(M * 2 * 4), o_s1 = take(M * 2 * 4);
+  const size_t o_y = take(M * D * 2);
   Workspace w;
   char* b = reinterpret_cast<char*>(base);
   w.x = reinterpret_cast<float*>(b + o_x);
@@ -52,6 +54,7 @@ Workspace carve(const vq_aggregator_cfg* c, void* base) {
   w.qkv = b + o_qkv;
   w.att = b + o_att;
   w.h = b + o_h;
+  w.y = b + o_y;
   w.stats[0] = reinterpret_cast<float*>(b + o_s0);
   w.stats[1] = reinterpret_cast<float*>(b + o_s1);
   w.total = off;
@@ -159,6 +162,82 @@ int run_block(const vq_aggregator_cfg* c, const vq_block_weights& bw, const vq_a
   return VQ_OK;
 }
 
+// The same block with the residual add DEFERRED into the LayerNorm pass that follows it (default schedule):
+//   [LN1 -> xn]  qkv  attention  proj -> y = ls1 (att Wp^T + b)      (plain bf16 epilogue: no f32 read-modify-write)
+//   x += y ; xn = LN2(x)                                              (one streaming row kernel)
+//   fc1 -> h     fc2 -> y = ls2 (h W2^T + b2)
+//   x += y ; xn = LN1_next(x)   (the NEXT block's first LayerNorm; add only at the end of a chain)
+// `first` = the block opens a chain (xn is not prepared yet); next_w / next_b = norm1 of the next block or nullptr.
+int run_block_deferred(const vq_aggregator_cfg* c, const vq_block_weights& bw, const vq_aggregator_weights* w,
+                       const Workspace& ws, long long M, int P, int gw, int n_seq, int seq_len, float eps, bool first,
+                       const float* next_w, const float* next_b, vq_stream_t stream) {
+  const int D = c->D;
+  int rc;
+  if (first) {
+    rc = vq_layernorm(ws.x, VQ_F32, ws.xn, VQ_BF16, bw.norm1_w, bw.norm1_b, M, D, eps, nullptr, nullptr, stream);
+    if (rc) return rc;
+  }
+  {
+    vq_gemm_desc g;
+    memset(&g, 0, sizeof(g));
+    g.M = (int)M; g.N = 3 * D; g.K = D;
+    g.A = ws.xn; g.lda = D;
+    g.B = bw.qkv_w; g.ldb = D;
+    g.C = ws.qkv; g.ldc = 3 * D; g.c_dtype = VQ_BF16;
+    g.epilogue = VQ_EPI_QKV_ROPE;
+    g.bias = bw.qkv_b;
+    g.tokens_per_frame = P; g.patch_start = c->n_special; g.grid_w = gw;
+    g.apply_qknorm_rope = bw.q_norm_w != nullptr;
+    g.qn_w = bw.q_norm_w; g.qn_b = bw.q_norm_b; g.kn_w = bw.k_norm_w; g.kn_b = bw.k_norm_b;
+    g.qk_eps = c->qk_eps;
+    g.q_scale = 1.4426950408889634f / 8.0f;
+    g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_positions = w->rope_max_pos + 1;
+    rc = vq_gemm(&g, stream);
+    if (rc) return rc;
+  }
+  rc = vq_attention_fwd_bounded(ws.qkv, ws.att, n_seq, seq_len, c->heads, bw.q_norm_w ? bw.qk_score_bound : 0.f, stream);
+  if (rc) return rc;
+  {
+    vq_gemm_desc g;
+    memset(&g, 0, sizeof(g));
+    g.M = (int)M; g.N = D; g.K = D;
+    g.A = ws.att; g.lda = D;
+    g.B = bw.proj_w; g.ldb = D;
+    g.C = ws.y; g.ldc = D; g.c_dtype = VQ_BF16;
+    g.epilogue = VQ_EPI_LINEAR;
+    g.bias = bw.proj_b; g.gamma = bw.ls1;
+    rc = vq_gemm(&g, stream);
+    if (rc) return rc;
+  }
+  rc = vq_residual_layernorm(ws.x, ws.y, ws.xn, bw.norm2_w, bw.norm2_b, M, D, eps, stream);
+  if (rc) return rc;
+  {
+    vq_gemm_desc g;
+    memset(&g, 0, sizeof(g));
+    g.M = (int)M; g.N = c->hidden; g.K = D;
+    g.A = ws.xn; g.lda = D;
+    g.B = bw.fc1_w; g.ldb = D;
+    g.C = ws.h; g.ldc = c->hidden; g.c_dtype = VQ_BF16;
+    g.epilogue = VQ_EPI_GELU;
+    g.bias = bw.fc1_b;
+    rc = vq_gemm(&g, stream);
+    if (rc) return rc;
+  }
+  {
+    vq_gemm_desc g;
+    memset(&g, 0, sizeof(g));
+    g.M = (int)M; g.N = D; g.K = c->hidden;
+    g.A = ws.h; g.lda = c->hidden;
+    g.B = bw.fc2_w; g.ldb = c->hidden;
+    g.C = ws.y; g.ldc = D; g.c_dtype = VQ_BF16;
+    g.epilogue = VQ_EPI_LINEAR;
+    g.bias = bw.fc2_b; g.gamma = bw.ls2;
+    rc = vq_gemm(&g, stream);
+    if (rc) return rc;
+  }
+  return vq_residual_layernorm(ws.x, ws.y, next_w ? ws.xn : nullptr, next_w, next_b, M, D, eps, stream);
+}
+
 }  // namespace
 
 extern "C" size_t vq_aggregator_workspace_bytes(const vq_aggregator_cfg* cfg) {
@@ -221,8 +300,16 @@ extern "C" int vq_aggregator_forward(const vq_aggregator_cfg* c, const vq_aggreg
     rc = vq_row_stats_cast(ws.x, ws.xn, ws.stats[0], ws.stats[1], M, D, stream);
     if (rc) return rc;
   }
+  const bool deferred = c->deferred_residual != 0 && !fold_stem && !fold_agg;
   for (int i = 0; i < w->n_stem; ++i) {
-    rc = run_block(c, w->stem_blocks[i], w, ws, M, P, gw, F, P, c->stem_eps, stream);
+    if (deferred) {
+      const bool last = i == w->n_stem - 1;
+      rc = run_block_deferred(c, w->stem_blocks[i], w, ws, M, P, gw, F, P, c->stem_eps, i == 0,
+                              last ? nullptr : w->stem_blocks[i + 1].norm1_w, last ? nullptr : w->stem_blocks[i + 1].norm1_b,
+                              stream);
+    } else {
+      rc = run_block(c, w->stem_blocks[i], w, ws, M, P, gw, F, P, c->stem_eps, stream);
+    }
     if (rc) return rc;
   }
   rc = vq_stem_finalize(ws.x, w->stem_norm_w, w->stem_norm_b, w->camera_token, w->register_token, M, D, P, c->S,
@@ -238,7 +325,11 @@ extern "C" int vq_aggregator_forward(const vq_aggregator_cfg* c, const vq_aggreg
   const long long SP = (long long)c->S * P;
   for (int i = 0; i < w->depth; ++i) {
     const bool last = i == w->depth - 1;
-    rc = run_block(c, w->frame_blocks[i], w, ws, M, P, gw, F, P, c->block_eps, stream);
+    if (deferred)
+      rc = run_block_deferred(c, w->frame_blocks[i], w, ws, M, P, gw, F, P, c->block_eps, i == 0,
+                              w->global_blocks[i].norm1_w, w->global_blocks[i].norm1_b, stream);
+    else
+      rc = run_block(c, w->frame_blocks[i], w, ws, M, P, gw, F, P, c->block_eps, stream);
     if (rc) return rc;
     if (out_all) {
       rc = vq_gather_tokens(ws.x, out_all[i], c->B, SP, (int)SP, D, 2 * D, 0, stream);
@@ -248,7 +339,12 @@ extern "C" int vq_aggregator_forward(const vq_aggregator_cfg* c, const vq_aggreg
       rc = vq_gather_tokens(ws.x, out_tokens, c->B, SP, n_take, D, 2 * D, 0, stream);
       if (rc) return rc;
     }
-    rc = run_block(c, w->global_blocks[i], w, ws, M, P, gw, c->B, (int)SP, c->block_eps, stream);
+    if (deferred)
+      rc = run_block_deferred(c, w->global_blocks[i], w, ws, M, P, gw, c->B, (int)SP, c->block_eps, false,
+                              last ? nullptr : w->frame_blocks[i + 1].norm1_w, last ? nullptr : w->frame_blocks[i + 1].norm1_b,
+                              stream);
+    else
+      rc = run_block(c, w->global_blocks[i], w, ws, M, P, gw, c->B, (int)SP, c->block_eps, stream);
     if (rc) return rc;
     if (out_all) {
       rc = vq_gather_tokens(ws.x, out_all[i], c->B, SP, (int)SP, D, 2 * D, D, stream);

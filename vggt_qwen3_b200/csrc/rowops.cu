@@ -180,6 +180,35 @@ layernorm_kernel(const void* __restrict__ in, void* __restrict__ out, const floa
   }
 }
 
+// Residual add fused with the LayerNorm that follows it: x += y (y = the bf16 branch output gamma_ls (acc + b) of the proj /
+// fc2 GEMM), then xn = LN(x) for the next GEMM.  The GEMM epilogue then is a plain bf16 store (no f32 read-modify-write
+// stalling its accumulator drain) and the f32 stream is touched by ONE streaming pass per half block:
+// 4 B read + 2 B read + 4 B write + 2 B write per element.  xn == nullptr: add only (end of a block chain).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+residual_layernorm_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ xn,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int D,
+                          float eps) {
+  pdl_launch_dependents();
+  pdl_wait();   // x and y come from the previous kernels
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[VEC][4];
+  load_row<VEC, true>(x, row, D, lane, v);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const uint2 t = *reinterpret_cast<const uint2*>(y + row * D + col);
+    v[i][0] += bf16_lo(t.x); v[i][1] += bf16_hi(t.x); v[i][2] += bf16_lo(t.y); v[i][3] += bf16_hi(t.y);
+    *reinterpret_cast<float4*>(x + row * D + col) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+  }
+  if (xn == nullptr) return;
+  float mean, rstd;
+  row_stats<VEC>(v, D, eps, mean, rstd);
+  norm_store_row<VEC, false>(xn, row, D, lane, v, mean, rstd, gamma, beta);
+}
+
 // Entry of a LayerNorm-folded chain: per-row (sum, sum of squares) + bf16 copy, one warp per row.
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -374,6 +403,34 @@ extern "C" int vq_layernorm(const void* in, int32_t in_dtype, void* out, int32_t
   if (i32 && o32) return launch_ln<true, true>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
   if (!i32 && !o32) return launch_ln<false, false>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
   return launch_ln<false, true>(in, out, gamma, beta, rows, D, eps, mean_out, rstd_out, stream);
+}
+
+extern "C" int vq_residual_layernorm(float* x, const void* y_bf16, void* xn_bf16, const float* gamma, const float* beta,
+                                     int64_t rows, int32_t D, float eps, vq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VQ_CHECK_ARG(x && y_bf16, "null pointer");
+  VQ_CHECK_ARG(!xn_bf16 || (gamma && beta), "LayerNorm output needs gamma and beta");
+  VQ_CHECK_ARG(rows > 0 && D > 0 && D % 128 == 0, "rows > 0 and D % 128 == 0 required");
+  const int warps = 8;
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(y_bf16);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(xn_bf16);
+  LaunchScope scope(kKindRow, xn ? "residual_layernorm" : "residual_add", (int)rows, D, 0, 0,
+                    (double)rows * D * (xn ? 12.0 : 10.0), stream);
+#define VQ_RL_CASE(V)                                                                                            \
+  case V:                                                                                                        \
+    VQ_CHECK_CUDA(launch_pdl(residual_layernorm_kernel<V>, dim3(grid), dim3(warps * 32), 0, stream, x, y, xn,    \
+                             gamma, beta, (long long)rows, D, eps));                                             \
+    break;
+  switch (D / 128) {
+    VQ_RL_CASE(1) VQ_RL_CASE(2) VQ_RL_CASE(3) VQ_RL_CASE(4) VQ_RL_CASE(6) VQ_RL_CASE(8)
+    default:
+      set_error("residual_layernorm: unsupported width");
+      return VQ_ERR_UNSUPPORTED;
+  }
+#undef VQ_RL_CASE
+  VQ_CHECK_CUDA(cudaGetLastError());
+  return VQ_OK;
 }
 
 extern "C" int vq_row_stats_cast(const float* x, void* xb_bf16, float* stats, float* stats_zero, int64_t rows, int32_t D,
