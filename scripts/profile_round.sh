@@ -1,21 +1,28 @@
 #!/bin/bash
-# Round profiling recipe (run under gpurun on ONE GPU):  scripts/profile_round.sh r01
-#  1. plain bench (must exit 0), 2. ncu launch list of one steady-state step, 3. ncu --set full of the top kernels
+# Round profiling recipe (run under gpurun on ONE GPU):  scripts/profile_round.sh r02
+#  1. plain bench (must exit 0), 2. ncu launch list of one steady-state c2 step, 3. ncu --set full of the top kernels
 #  (each only after the same command has exited 0 without ncu).  Reduce here with scripts/ncu_summary.py.
 set -u
-R=${1:-r01}
+R=${1:-r02}
 O=gpurun_out
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profile-steps 0"
-$BENCH > $O/${R}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 2172 -c 724 --csv --log-file $O/${R}_launches.csv \
+mkdir -p $O
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-extra-workloads --profile-steps 0"
+# launches per step: from a plain run's own count
+$BENCH > $O/${R}_plain.log 2>&1 || { echo "plain bench failed"; tail -5 $O/${R}_plain.log; exit 1; }
+L=$(python -c "import json;print(json.loads(open('$O/${R}_plain.log').read().strip().splitlines()[-1])['gpu_launches_per_step'])")
+echo "launches per step: $L"
+# skip the 3 warm-up steps + the first timed step, capture the second timed step
+ncu --metrics gpu__time_duration.sum --clock-control none -s $((4 * L)) -c $L --csv --log-file $O/${R}_launches.csv \
     $BENCH > $O/${R}_launches_run.log 2>&1
-tail -2 $O/${R}_plain.log | cut -c1-300
-for c in attn_frame:attention_fwd attn_frame32_m:attention_fwd attn_global8x4_m:attention_fwd gemm_t_fc1:gemm_kernel \
-         gemm_t_fc2:gemm_kernel gemm_t_qkvrope:gemm_kernel gemm_t_proj:gemm_kernel; do
-  CASE=${c%%:*}; K=${c##*:}
-  python scripts/gpu_bringup.py $CASE > $O/${R}_${CASE}_plain.log 2>&1 &&
+tail -1 $O/${R}_plain.log | cut -c1-200
+for c in "gemm_fc1_gelu:gemm_kernel:gpu_bringup.py gemm_t_fc1" "gemm_fc2:gemm_kernel:gpu_bringup.py gemm_t_fc2" \
+         "attn_bounded_frame8:attention_fwd_bounded:attn_case.py 8 1374 1" \
+         "attn_bounded_global8x4:attention_fwd_bounded:attn_case.py 4 10992 1" \
+         "attn_checked_frame8:attention_fwd_wide:attn_case.py 8 1374 0"; do
+  CASE=${c%%:*}; REST=${c#*:}; K=${REST%%:*}; CMD=${REST#*:}
+  python scripts/$CMD > $O/${R}_${CASE}_plain.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o $O/${R}_${CASE} \
-      python scripts/gpu_bringup.py $CASE > $O/${R}_${CASE}_ncu.log 2>&1
+      python scripts/$CMD > $O/${R}_${CASE}_ncu.log 2>&1
   tail -1 $O/${R}_${CASE}_plain.log | cut -c1-160
 done
 ls -la $O | grep ${R}_
