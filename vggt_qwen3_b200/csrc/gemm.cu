@@ -216,8 +216,11 @@ __device__ __forceinline__ void loadv(const void* base, long long off, float* v)
   }
 }
 
-// MODE: VQ_EPI_* ; OUT_F32: C/add dtype
-template <int BLOCK_N, int MODE, bool OUT_F32, int CG>
+// MODE: VQ_EPI_* ; OUT_F32: C/add dtype ; EX: the rarely used epilogue extras (dropout, LayerNorm folding, row statistics /
+// bf16 copy, K-sliced tail tiles) are compiled in.  They live in a separate instantiation because the fully unrolled
+// epilogue is instruction-cache bound: with everything compiled into one kernel the f32-residual instance was 173 KB
+// of SASS and ncu's top stall after `barrier` was `no_instruction` (profiles/r02_gemm_fc1_gelu.txt).
+template <int BLOCK_N, int MODE, bool OUT_F32, int CG, bool EX>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmArgs g) {
@@ -437,7 +440,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       GemmWork w0;
       if (gemm_work(g, 0, first_tile, tile_stride, num_kb, w0) && w0.slice <= 0) prefetch_add(w0.tile);
     }
-    if constexpr (MODE == VQ_EPI_LINEAR && OUT_F32) {
+    if constexpr (EX && MODE == VQ_EPI_LINEAR && OUT_F32) {
       // the statistics buffer of the NEXT producer: its last readers finished before this grid's dependency resolved
       if (g.stats_zero) {
         const int n2 = 2 * g.M;
@@ -492,7 +495,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // LayerNorm folded into this GEMM: A held the raw rows x, W the gamma-scaled weight W', so
             // LN(x) W^T + b = rstd (x W'^T - mean colsum(W')) + (W beta + b); the last term arrives as the bias
             float ln_mean = 0.f, ln_rstd = 1.f;
-            if (g.ln_stats && row_ok) {
+            if (EX && g.ln_stats && row_ok) {
               const float2 st = *reinterpret_cast<const float2*>(g.ln_stats + 2 * (long long)m);
               ln_mean = st.x * g.ln_inv_dim;
               ln_rstd = rsqrtf(fmaxf(st.y * g.ln_inv_dim - ln_mean * ln_mean, 0.f) + g.ln_eps);
@@ -501,7 +504,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t r[32];
             tmem_ld32(taddr + hh * 64, r);
             tmem_wait_ld();
-            if (g.ln_stats) {
+            if (EX && g.ln_stats) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 v[i] = (__uint_as_float(r[i]) - ln_mean * cs[i]) * ln_rstd + my_vec[hh * 64 + i];
@@ -511,7 +514,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             tmem_ld32(taddr + hh * 64 + 32, r);
             tmem_wait_ld();
-            if (g.ln_stats) {
+            if (EX && g.ln_stats) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 v[32 + i] = (__uint_as_float(r[i]) - ln_mean * cs[32 + i]) * ln_rstd + my_vec[hh * 64 + 32 + i];
@@ -619,7 +622,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         constexpr int kChunks = kHalfN / 32;
         // LayerNorm folding, consumer side: per-row mean / rstd of the rows this thread touches
         float ln_mean[kPasses], ln_rstd[kPasses];
-        if constexpr (MODE == VQ_EPI_GELU || MODE == VQ_EPI_LINEAR) {
+        if constexpr (EX && (MODE == VQ_EPI_GELU || MODE == VQ_EPI_LINEAR)) {
           if (g.ln_stats) {
 #pragma unroll
             for (int ps = 0; ps < kPasses; ++ps) {
@@ -641,7 +644,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // epilogue -- a fixed summation order, so the result does not depend on timing.
         const int tail_idx = tile - g.full_tiles;
         constexpr int kWarpWs = kChunks * 1024;   // floats per warp and partial tile
-        if (wk.slice > 0) {
+        if (EX && wk.slice > 0) {
           float* wsp = g.splitk_ws +
                        ((((size_t)tail_idx * (g.tail_split - 1) + (wk.slice - 1)) * CG + cta_rank) * 8 + warp) * kWarpWs;
           if (n_base < g.N) tmem_ld32(taddr, acc[0]);
@@ -666,7 +669,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           continue;
         }
-        const bool owner = wk.slice == 0;
+        const bool owner = EX && wk.slice == 0;
         if (owner) {
           if (lane == 0) {
             const unsigned want = (unsigned)(g.tail_split - 1) * CG * 8;
@@ -680,7 +683,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
         }
         if (n_base < g.N) tmem_ld32(taddr, acc[0]);
-#pragma unroll
+#pragma unroll 2   // two copies keep the accumulator double buffer statically indexed; more only bloats the code
         for (int ch = 0; ch < kChunks; ++ch) {
           const int n0 = n_base + ch * 32;
           if (n0 >= g.N) break;  // warp-uniform
@@ -757,7 +760,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[e + 2] = a4.z * g.alpha + bv[e + 2];
               v[e + 3] = a4.w * g.alpha + bv[e + 3];
             }
-            if constexpr (MODE == VQ_EPI_GELU || MODE == VQ_EPI_LINEAR) {
+            if constexpr (EX && (MODE == VQ_EPI_GELU || MODE == VQ_EPI_LINEAR)) {
               if (g.ln_stats) {   // LN(x) W^T + b = rstd (x W'^T - mean colsum(W')) + b'   (gv = colsum, bv = b')
 #pragma unroll
                 for (int e = 0; e < kVec; ++e)
@@ -784,7 +787,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int e = 0; e < kVec; ++e) v[e] += auxv[ps][e];
             }
-            if constexpr (MODE == VQ_EPI_LINEAR || MODE == VQ_EPI_GELU || MODE == VQ_EPI_GELU_BWD) {
+            if constexpr (EX && (MODE == VQ_EPI_LINEAR || MODE == VQ_EPI_GELU || MODE == VQ_EPI_GELU_BWD)) {
               if (g.drop.thr) {   // train-mode dropout: mask regenerated from (row, column), see philox.cuh
                 const int m = m_warp0 + ps * kRowsPerPass + rsub;
                 const uint32_t keep =
@@ -802,7 +805,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int e = 0; e < kVec; ++e) v[e] += addv[ps][e];
             }
             storev<OUT_F32>(g.C, orow[ps] * g.ldc + c_c + ncol, v);
-            if constexpr (MODE == VQ_EPI_LINEAR && OUT_F32) {
+            if constexpr (EX && MODE == VQ_EPI_LINEAR && OUT_F32) {
               if (g.c_copy) {      // bf16 copy of the rows: the A operand of the LayerNorm-folded GEMM that follows
                 uint2 u;
                 u.x = pack_bf16x2(v[0], v[1]);
@@ -816,7 +819,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-        if constexpr (MODE == VQ_EPI_LINEAR && OUT_F32) {
+        if constexpr (EX && MODE == VQ_EPI_LINEAR && OUT_F32) {
           if (g.stats_out) {
             // the kLanesPerRow lanes that share a row combine, then one pair of atomics per row and warp
 #pragma unroll
@@ -836,7 +839,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
-      if constexpr (MODE != VQ_EPI_QKV_ROPE) {
+      if constexpr (EX && MODE != VQ_EPI_QKV_ROPE) {
         if (wk.slice == 0) {   // the last owner warp to finish re-arms the tile's flags for the next launch
           __syncwarp();
           if (lane == 0) {
@@ -879,10 +882,10 @@ static int g_gemm_tail_split = [] {
   return v < 0 ? 0 : v > 8 ? 8 : v;
 }();
 
-template <int BLOCK_N, int MODE, bool OUT_F32, int CG>
+template <int BLOCK_N, int MODE, bool OUT_F32, int CG, bool EX>
 static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
-  auto kern = gemm_kernel<BLOCK_N, MODE, OUT_F32, CG>;
+  auto kern = gemm_kernel<BLOCK_N, MODE, OUT_F32, CG, EX>;
   VQ_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes));
   const int sms = num_sms();
   const int units = CG == 2 ? sms / 2 : sms;                     // CTAs (pairs) of a persistent grid
@@ -897,7 +900,7 @@ static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmAr
   g.splitk_flags = nullptr;
   const int n_tail = g.total_tiles - g.full_tiles;
   const int split_on = g_gemm_tail_split;
-  if (MODE != VQ_EPI_QKV_ROPE && split_on && n_tail > 0 && g.total_tiles == g.m_tiles * g.n_tiles) {
+  if (EX && MODE != VQ_EPI_QKV_ROPE && split_on > 1 && n_tail > 0 && g.total_tiles == g.m_tiles * g.n_tiles) {
     const int num_kb = (g.K + kBlockK - 1) / kBlockK;
     int split = units / n_tail;
     if (split > split_on) split = split_on;
@@ -944,8 +947,14 @@ static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmAr
 template <int BLOCK_N, int MODE, bool OUT_F32>
 static int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g, cudaStream_t stream,
                        int cta_group) {
-  if (cta_group == 2) return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 2>(tmA, tmB, g, stream);
-  return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 1>(tmA, tmB, g, stream);
+  // the lean instantiation unless this launch uses one of the epilogue extras (or tail splitting is switched on)
+  const bool ex = g.drop.thr != 0 || g.ln_stats || g.stats_out || g.stats_zero || g.c_copy || g_gemm_tail_split > 1;
+  if (ex) {
+    if (cta_group == 2) return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 2, true>(tmA, tmB, g, stream);
+    return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 1, true>(tmA, tmB, g, stream);
+  }
+  if (cta_group == 2) return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 2, false>(tmA, tmB, g, stream);
+  return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 1, false>(tmA, tmB, g, stream);
 }
 
 static inline bool fits_i32(long long v) { return v >= INT32_MIN && v <= INT32_MAX; }
