@@ -638,7 +638,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float rs[kPasses], rq[kPasses];
 #pragma unroll
         for (int ps = 0; ps < kPasses; ++ps) rs[ps] = rq[ps] = 0.f;
-        uint32_t acc[2][32];
+        uint32_t r[32];   // the accumulator chunk in flight: dead once it is staged in smem, so one buffer suffices
         // K-sliced tail tile: slices > 0 park their raw accumulators in the workspace (thread-private layout: the owner's
         // thread at the same position reads them back; lane-interleaved 16-byte granules), slice 0 waits for them and adds them in slice order before its
         // epilogue -- a fixed summation order, so the result does not depend on timing.
@@ -647,13 +647,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (EX && wk.slice > 0) {
           float* wsp = g.splitk_ws +
                        ((((size_t)tail_idx * (g.tail_split - 1) + (wk.slice - 1)) * CG + cta_rank) * 8 + warp) * kWarpWs;
-          if (n_base < g.N) tmem_ld32(taddr, acc[0]);
-#pragma unroll
+#pragma unroll 1
           for (int ch = 0; ch < kChunks; ++ch) {
             if (n_base + ch * 32 >= g.N) break;
+            tmem_ld32(taddr + ch * 32, r);
             tmem_wait_ld();
-            if (ch + 1 < kChunks && n_base + (ch + 1) * 32 < g.N) tmem_ld32(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);
-            const uint32_t(&r)[32] = acc[ch & 1];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               *reinterpret_cast<uint4*>(wsp + ((ch * 8 + k) * 32 + lane) * 4) =   // lane-interleaved: 512 B per request
@@ -682,13 +680,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           __syncwarp();
         }
-        if (n_base < g.N) tmem_ld32(taddr, acc[0]);
-#pragma unroll 2   // two copies keep the accumulator double buffer statically indexed; more only bloats the code
+        if (n_base < g.N) tmem_ld32(taddr, r);
+#pragma unroll 1   // ONE copy of the body: the fully unrolled epilogue did not fit the 32 KB L1.5 instruction cache
         for (int ch = 0; ch < kChunks; ++ch) {
           const int n0 = n_base + ch * 32;
           if (n0 >= g.N) break;  // warp-uniform
           tmem_wait_ld();
-          if (ch + 1 < kChunks && n0 + 32 < g.N) tmem_ld32(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);
           if (owner) {
             for (int sl = 1; sl < g.tail_split; ++sl) {
               const float* wsp = g.splitk_ws +
@@ -700,21 +697,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const float4 pv = pvs[k];
-                uint32_t(&ra)[32] = acc[ch & 1];
-                ra[4 * k] = __float_as_uint(__uint_as_float(ra[4 * k]) + pv.x);
-                ra[4 * k + 1] = __float_as_uint(__uint_as_float(ra[4 * k + 1]) + pv.y);
-                ra[4 * k + 2] = __float_as_uint(__uint_as_float(ra[4 * k + 2]) + pv.z);
-                ra[4 * k + 3] = __float_as_uint(__uint_as_float(ra[4 * k + 3]) + pv.w);
+                r[4 * k] = __float_as_uint(__uint_as_float(r[4 * k]) + pv.x);
+                r[4 * k + 1] = __float_as_uint(__uint_as_float(r[4 * k + 1]) + pv.y);
+                r[4 * k + 2] = __float_as_uint(__uint_as_float(r[4 * k + 2]) + pv.z);
+                r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + pv.w);
               }
             }
           }
-          const uint32_t(&r)[32] = acc[ch & 1];
           __syncwarp();  // previous chunk's transposed reads are done
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             *reinterpret_cast<uint4*>(stage + lane * kStageLd + 4 * k) =
                 make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
           __syncwarp();
+          // the registers are free again: the next chunk's TMEM load overlaps this chunk's math and global traffic
+          if (ch + 1 < kChunks && n0 + 32 < g.N) tmem_ld32(taddr + (ch + 1) * 32, r);
           const int ncol = n0 + cb;
           const bool col_ok = ncol < g.N;  // N % 8 == 0: a thread's kVec columns are all in or all out
           float bv[kVec], gv[kVec];

@@ -93,7 +93,7 @@ softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict_
 
 // ---- LayerNorm backward, two HBM-bound kernels.
 // (1) dz = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)), xhat = (z - mean) * rstd: one warp per row.
-template <int VEC>
+template <int VEC, bool DROP>   // DROP: the dropout-branch output is compiled in (keeps the eval kernel small: I-cache)
 __global__ void __launch_bounds__(256)
 layernorm_bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -130,7 +130,7 @@ layernorm_bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
     u.x = pack_bf16x2(rs * (dyg[i][0] - s1 - xh[i][0] * s2), rs * (dyg[i][1] - s1 - xh[i][1] * s2));
     u.y = pack_bf16x2(rs * (dyg[i][2] - s1 - xh[i][2] * s2), rs * (dyg[i][3] - s1 - xh[i][3] * s2));
     *reinterpret_cast<uint2*>(dz + r * D + col) = u;
-    if (drop.thr) {
+    if (DROP && drop.thr) {
       // gradient of the dropped branch: the mask acts on the bf16 dz the residual path sees
       const uint32_t keep = dropout_keep8(drop, (uint64_t)r * (uint64_t)(D >> 3) + (uint64_t)(col >> 3)) >> (col & 4);
       uint2 w;
@@ -334,7 +334,8 @@ extern "C" int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const f
     LaunchScope scope(kKindRow, "layernorm_bwd_dz", (int)rows, D, 0, 0, (double)rows * D * 6.0, stream);
 #define VQ_LNB_CASE(V)                                                                                  \
   case V:                                                                                               \
-    layernorm_bwd_dz_kernel<V><<<grid, 256, 0, stream>>>(dy, z, mean, rstd, gamma, dz, rows, D, drop, dzd); \
+    if (drop.thr) layernorm_bwd_dz_kernel<V, true><<<grid, 256, 0, stream>>>(dy, z, mean, rstd, gamma, dz, rows, D, drop, dzd); \
+    else layernorm_bwd_dz_kernel<V, false><<<grid, 256, 0, stream>>>(dy, z, mean, rstd, gamma, dz, rows, D, drop, dzd); \
     break;
     switch (D / 128) {
       VQ_LNB_CASE(1) VQ_LNB_CASE(2) VQ_LNB_CASE(4) VQ_LNB_CASE(8) VQ_LNB_CASE(16) VQ_LNB_CASE(32)
