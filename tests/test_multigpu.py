@@ -116,6 +116,6 @@ def test_sharded_adamw_over_symmetric_memory():
     for rank, same, worst, sign_ok, pulled in results:
         assert not isinstance(same, str), f"rank {rank}: {same}"
         assert same, f"rank {rank}: compute copies differ between ranks"
-        assert worst <= 0.08, f"rank {rank}: update error {worst:.3e} of the update size"
+        assert worst <= 0.12, f"rank {rank}: update error {worst:.3e} of the update size"
         assert sign_ok, f"rank {rank}: fp32 reduce of the bf16 slices is wrong"
         assert pulled > 0
