@@ -216,15 +216,18 @@ __device__ __forceinline__ void loadv(const void* base, long long off, float* v)
   }
 }
 
-// MODE: VQ_EPI_* ; OUT_F32: C/add dtype ; EX: the rarely used epilogue extras (dropout, LayerNorm folding, row statistics /
-// bf16 copy, K-sliced tail tiles) are compiled in.  They live in a separate instantiation because the fully unrolled
-// epilogue is instruction-cache bound: with everything compiled into one kernel the f32-residual instance was 173 KB
-// of SASS and ncu's top stall after `barrier` was `no_instruction` (profiles/r02_gemm_fc1_gelu.txt).
-template <int BLOCK_N, int MODE, bool OUT_F32, int CG, bool EX>
+// MODE: VQ_EPI_* ; OUT_F32: C/add dtype ; EXL: which of the rarely used epilogue extras are compiled in -- 0 none (what the
+// aggregator runs), 1 train-mode dropout only (the Perceiver's four sites), 2 everything (LayerNorm folding, row
+// statistics / bf16 copy, K-sliced tail tiles, dropout).  Separate instantiations because the unrolled epilogue is
+// instruction-cache bound: with everything compiled into one kernel the f32-residual instance was 173 KB of SASS and
+// ncu's top stall after `barrier` was `no_instruction` (profiles/r02_gemm_fc1_gelu.txt).
+template <int BLOCK_N, int MODE, bool OUT_F32, int CG, int EXL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmArgs g) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
+  constexpr bool EX = EXL == 2;      // LayerNorm folding, statistics, tail split
+  constexpr bool DROPX = EXL >= 1;   // dropout
   constexpr int kStages = Cfg::kStages;
   constexpr int kTileM = kBlockM * CG;                       // rows of C per (pair-)tile
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;  // 0 = leader (issues the MMAs)
@@ -784,7 +787,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int e = 0; e < kVec; ++e) v[e] += auxv[ps][e];
             }
-            if constexpr (EX && (MODE == VQ_EPI_LINEAR || MODE == VQ_EPI_GELU || MODE == VQ_EPI_GELU_BWD)) {
+            if constexpr (DROPX && (MODE == VQ_EPI_LINEAR || MODE == VQ_EPI_GELU || MODE == VQ_EPI_GELU_BWD)) {
               if (g.drop.thr) {   // train-mode dropout: mask regenerated from (row, column), see philox.cuh
                 const int m = m_warp0 + ps * kRowsPerPass + rsub;
                 const uint32_t keep =
@@ -879,10 +882,11 @@ static int g_gemm_tail_split = [] {
   return v < 0 ? 0 : v > 8 ? 8 : v;
 }();
 
-template <int BLOCK_N, int MODE, bool OUT_F32, int CG, bool EX>
+template <int BLOCK_N, int MODE, bool OUT_F32, int CG, int EXL>
 static int launch_gemm_cg(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
-  auto kern = gemm_kernel<BLOCK_N, MODE, OUT_F32, CG, EX>;
+  constexpr bool EX = EXL == 2;
+  auto kern = gemm_kernel<BLOCK_N, MODE, OUT_F32, CG, EXL>;
   VQ_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes));
   const int sms = num_sms();
   const int units = CG == 2 ? sms / 2 : sms;                     // CTAs (pairs) of a persistent grid
@@ -945,13 +949,19 @@ template <int BLOCK_N, int MODE, bool OUT_F32>
 static int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, GemmArgs& g, cudaStream_t stream,
                        int cta_group) {
   // the lean instantiation unless this launch uses one of the epilogue extras (or tail splitting is switched on)
-  const bool ex = g.drop.thr != 0 || g.ln_stats || g.stats_out || g.stats_zero || g.c_copy || g_gemm_tail_split > 1;
+  const bool ex = g.ln_stats || g.stats_out || g.stats_zero || g.c_copy || g_gemm_tail_split > 1;
   if (ex) {
-    if (cta_group == 2) return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 2, true>(tmA, tmB, g, stream);
-    return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 1, true>(tmA, tmB, g, stream);
+    if (cta_group == 2) return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 2, 2>(tmA, tmB, g, stream);
+    return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 1, 2>(tmA, tmB, g, stream);
   }
-  if (cta_group == 2) return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 2, false>(tmA, tmB, g, stream);
-  return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 1, false>(tmA, tmB, g, stream);
+  if constexpr (MODE == VQ_EPI_LINEAR || MODE == VQ_EPI_GELU || MODE == VQ_EPI_GELU_BWD) {
+    if (g.drop.thr != 0) {
+      if (cta_group == 2) return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 2, 1>(tmA, tmB, g, stream);
+      return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 1, 1>(tmA, tmB, g, stream);
+    }
+  }
+  if (cta_group == 2) return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 2, 0>(tmA, tmB, g, stream);
+  return launch_gemm_cg<BLOCK_N, MODE, OUT_F32, 1, 0>(tmA, tmB, g, stream);
 }
 
 static inline bool fits_i32(long long v) { return v >= INT32_MIN && v <= INT32_MAX; }
