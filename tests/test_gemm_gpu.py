@@ -89,11 +89,33 @@ def test_gemm_gelu_backward():
 @pytest.mark.parametrize("frames,grid,heads", [(3, 6, 2), (2, 37, 4), (5, 9, 16)])
 def test_gemm_qkv_qknorm_rope_epilogue(frames, grid, heads):
     """qkv projection with the fused per-head QK LayerNorm(64) + 2-D RoPE + q pre-scale ([UPSTREAM]
-    vggt/layers/attention.py q_norm / k_norm, vggt/layers/rope.py) against the oracle's rope_2d on torch fp32."""
-    from scripts.gpu_bringup import case_qkv_rope
+    vggt/layers/attention.py q_norm / k_norm, vggt/layers/rope.py) against the ORACLE's own functions
+    (oracle.aggregator_ref.rope_tables / rope_2d / token_positions) evaluated in fp32 on the same bf16-rounded operands."""
+    from oracle import aggregator_ref as A
+    from vggt_qwen3_b200 import ops
 
-    ok, msg = case_qkv_rope(frames, grid, heads)
-    assert ok, msg
+    g = torch.Generator(device="cuda").manual_seed(5)
+    D, P = heads * 64, 5 + grid * grid
+    M = frames * P
+    x = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(3 * D, D, device="cuda", generator=g) / math.sqrt(D)).bfloat16()
+    bias = torch.randn(3 * D, device="cuda", generator=g) * 0.1
+    qn_w, kn_w = (torch.rand(64, device="cuda", generator=g) + 0.5 for _ in range(2))
+    qn_b, kn_b = (torch.randn(64, device="cuda", generator=g) * 0.1 for _ in range(2))
+    cos, sin = (t.cuda().contiguous() for t in A.rope_tables(grid, 64, 100.0))
+    q_scale = math.log2(math.e) / 8.0
+    extra = dict(tokens_per_frame=P, patch_start=5, grid_w=grid, apply_qknorm_rope=1, qn_w=qn_w, qn_b=qn_b, kn_w=kn_w,
+                 kn_b=kn_b, qk_eps=1e-5, q_scale=q_scale, rope_cos=cos, rope_sin=sin, rope_positions=grid + 1)
+    out = ops.gemm(x, w, bias=bias, epilogue=ops.EPI_QKV_ROPE, extra=extra)
+    torch.cuda.synchronize()
+    qkv = (x.float() @ w.float().t() + bias).view(frames, P, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    q = torch.nn.functional.layer_norm(qkv[0], (64,), qn_w, qn_b, 1e-5)
+    k = torch.nn.functional.layer_norm(qkv[1], (64,), kn_w, kn_b, 1e-5)
+    pos = A.token_positions(grid, grid, 5).cuda()[None].expand(frames, P, 2)
+    q = A.rope_2d(q, pos, cos, sin) * q_scale
+    k = A.rope_2d(k, pos, cos, sin)
+    ref = torch.stack([q, k, qkv[2]], 0).permute(1, 3, 0, 2, 4).reshape(M, 3 * D)
+    assert _rel(out, ref) < 1e-2
 
 
 @pytest.mark.parametrize("M,N,K,f32", [(300, 512, 256, False), (1024, 4096, 1024, False), (260, 256, 128, True)])

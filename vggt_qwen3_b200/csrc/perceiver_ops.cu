@@ -347,8 +347,11 @@ extern "C" int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const f
   }
   VQ_CHECK_CUDA(cudaGetLastError());
   {
-    const int rows_per_cta = 32;
-    dim3 grid((D / 8 + 127) / 128, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
+    // enough CTAs to fill the machine: with 1024 rows x 4096 columns 32 rows per CTA gave 128 CTAs of 128 threads
+    const int col_ctas = (D / 8 + 127) / 128;
+    int rows_per_cta = 32;
+    while (rows_per_cta > 4 && (long long)col_ctas * ((rows + rows_per_cta - 1) / rows_per_cta) < 4LL * 148) rows_per_cta /= 2;
+    dim3 grid(col_ctas, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
     LaunchScope scope(kKindRow, "layernorm_bwd_affine", (int)rows, D, 0, 0, (double)rows * D * 4.0, stream);
     layernorm_bwd_affine_kernel<<<grid, 128, 0, stream>>>(dy, z, mean, rstd, dgamma, dbeta, rows, D, rows_per_cta);
   }
@@ -361,9 +364,11 @@ extern "C" int vq_colsum(const void* x, int32_t dtype, float* out, int64_t rows,
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VQ_CHECK_ARG(x && out && rows > 0 && N > 0 && ld >= N, "colsum arguments");
   VQ_CHECK_ARG(N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0, "colsum: 16-byte rows");
-  const int rows_per_cta = 32;
   const int per = dtype == VQ_F32 ? 4 : 8;
-  dim3 grid((N / per + 127) / 128, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
+  const int col_ctas = (N / per + 127) / 128;
+  int rows_per_cta = 32;   // fewer rows per CTA while the grid would not fill the machine (1024 x 4096: 128 CTAs at 32)
+  while (rows_per_cta > 4 && (long long)col_ctas * ((rows + rows_per_cta - 1) / rows_per_cta) < 4LL * 148) rows_per_cta /= 2;
+  dim3 grid(col_ctas, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
   LaunchScope scope(kKindRow, "colsum", (int)rows, N, 0, 0, (double)rows * N * (dtype == VQ_F32 ? 4.0 : 2.0), stream);
   if (dtype == VQ_F32) colsum_kernel<true><<<grid, 128, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
   else colsum_kernel<false><<<grid, 128, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);

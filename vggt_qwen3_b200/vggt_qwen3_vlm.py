@@ -128,11 +128,18 @@ class VGGTQwen3VLM(nn.Module):
             agg = agg.reshape(images.shape[0], -1, agg.shape[-1])
         return agg[:, : self.num_vis_tokens, :]
 
+    def _projector_input(self, tokens: torch.Tensor) -> torch.Tensor:
+        """The reference casts the aggregator tokens to the projector's parameter dtype (:159-160).  The sm_100a projector
+        consumes bf16 tokens as they come out of the aggregator kernels (a cast to f32 and back would be two ATen
+        launches for nothing); any other projector module gets the reference's cast."""
+        if isinstance(self.projector, PerceiverProjector):
+            return tokens
+        return tokens.to(dtype=self.projector.in_proj.weight.dtype)
+
     @torch.no_grad()
     def encode_images(self, images: torch.Tensor) -> torch.Tensor:
         """images [B,V,C,H,W] -> [B, num_vis_tokens, hidden]; like the reference the whole call is under no_grad."""
-        agg = self._vision_tokens(images)
-        return self.projector(agg.to(dtype=self.projector.in_proj.weight.dtype))
+        return self.projector(self._projector_input(self._vision_tokens(images)))
 
     def encode_images_trainable(self, images: torch.Tensor) -> torch.Tensor:
         """Same tokens, but the projector runs under autograd (the frozen aggregator stays under no_grad), so that
@@ -142,9 +149,9 @@ class VGGTQwen3VLM(nn.Module):
     @torch.no_grad()
     def encode_image_tokens(self, images: torch.Tensor) -> torch.Tensor:
         """The frozen half of `encode_images_trainable` (reference :140-160): aggregator tokens [B, num_vis_tokens,
-        2048] in the projector's input dtype.  Independent of the projector weights, so a data-parallel trainer can
+        2048] as the projector consumes them (bf16 for the sm_100a projector).  Independent of the projector weights, so a data-parallel trainer can
         run it for step i+1 while the gradient all-reduce of step i is still in flight (bench.py does)."""
-        return self._vision_tokens(images).to(dtype=self.projector.in_proj.weight.dtype)
+        return self._projector_input(self._vision_tokens(images))
 
     def project_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
         """The trainable half (reference :162): `self.projector(tokens)` under autograd."""
