@@ -54,6 +54,13 @@ def case_gemm(M, N, K, a_major=0, b_major=0, epi="linear", out_f32=False, timing
         kw = dict(bias=bias, epilogue=ops.EPI_GELU, aux=aux)
         pre = ref + bias
         ref = torch.nn.functional.gelu(pre)
+    elif epi == "gelu_noaux":
+        kw = dict(bias=bias, epilogue=ops.EPI_GELU)
+        ref = torch.nn.functional.gelu(ref + bias)
+    elif epi == "ls_bf16":      # LayerScale-d branch output, bf16, no residual (deferred-residual schedule)
+        gamma = torch.rand(N, device="cuda", generator=g)
+        kw = dict(bias=bias, gamma=gamma)
+        ref = gamma * (ref + bias)
     elif epi == "lsres":
         gamma = torch.rand(N, device="cuda", generator=g)
         res = torch.randn(M, N, device="cuda", generator=g)
@@ -224,6 +231,9 @@ CASES = {
     # --- timing at the aggregator shapes (c2: M = 8*1374)
     "gemm_t_qkvshape": lambda: case_gemm(10992, 3072, 1024, timing=True),
     "gemm_t_fc1": lambda: case_gemm(10992, 4096, 1024, epi="gelu", timing=True),
+    "gemm_t_fc1_noaux": lambda: case_gemm(10992, 4096, 1024, epi="gelu_noaux", timing=True),   # as the aggregator runs it
+    "gemm_t_proj_bf16": lambda: case_gemm(10992, 1024, 1024, epi="ls_bf16", timing=True),      # deferred-residual schedule
+    "gemm_t_fc2_bf16": lambda: case_gemm(10992, 1024, 4096, epi="ls_bf16", timing=True),
     "gemm_t_fc2": lambda: case_gemm(10992, 1024, 4096, epi="lsres", out_f32=True, timing=True),
     "gemm_t_proj": lambda: case_gemm(10992, 1024, 1024, epi="lsres", out_f32=True, timing=True),
     "gemm_t_8k": lambda: case_gemm(8192, 8192, 8192, timing=True),

@@ -15,7 +15,8 @@ echo "launches per step: $L"
 ncu --metrics gpu__time_duration.sum --clock-control none -s $((4 * L)) -c $L --csv --log-file $O/${R}_launches.csv \
     $BENCH > $O/${R}_launches_run.log 2>&1
 tail -1 $O/${R}_plain.log | cut -c1-200
-for c in "gemm_fc1_gelu:gemm_kernel:gpu_bringup.py gemm_t_fc1" "gemm_fc2:gemm_kernel:gpu_bringup.py gemm_t_fc2" \
+for c in "gemm_fc1_gelu:gemm_kernel:gpu_bringup.py gemm_t_fc1_noaux" "gemm_fc2:gemm_kernel:gpu_bringup.py gemm_t_fc2_bf16" \
+         "gemm_proj:gemm_kernel:gpu_bringup.py gemm_t_proj_bf16" \
          "attn_bounded_frame8:attention_fwd_bounded:attn_case.py 8 1374 1" \
          "attn_bounded_global8x4:attention_fwd_bounded:attn_case.py 4 10992 1" \
          "attn_checked_frame8:attention_fwd_wide:attn_case.py 8 1374 0"; do

@@ -66,3 +66,27 @@ def test_committed_round_line_carries_every_contract_key():
     assert d["warmup"] >= 3 and d["dtype"] == "bf16" and "model" not in d["config"]
     c2 = json.loads((ROOT / "profiles" / "r01_bench_c2.json").read_text())
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c2["cpu_baseline"])
+
+
+def test_round2_line_carries_the_extended_contract():
+    """The committed round-2 default line: training step with optimizer and dropout in the timed region, uint8 e2e input,
+    the full result read back, c3 / c4 in the same line, the GPU-eager bar and the CPU baseline."""
+    d = json.loads([l for l in (ROOT / "profiles" / "r02_bench_c2.json").read_text().splitlines() if l.startswith("{")][-1])
+    assert BASE_KEYS | {"clocks", "gpu_launches", "roofline", "workloads", "gpu_eager_bf16", "cpu_baseline"} <= set(d)
+    assert d["config"]["workload"].startswith("c2") and "AdamW" in d["config"]["optimizer"]
+    assert "train mode" in d["config"]["dropout"] and "model" not in d["config"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 8 * 518 * 518 * 3            # uint8 views
+    assert d["e2e"]["d2h_bytes_per_step"] == 8 * 128 * 2560 * 4            # the projected tokens, not a checksum
+    assert d["e2e"]["value"] != d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and r["traffic"] > 0
+    assert set(d["workloads"]) == {"c3", "c4"}
+    for w in d["workloads"].values():
+        assert w["value"] > 0 and w["roofline"]["frac"] > 0 and w["e2e"]["h2d_bytes_per_step"] > 0
+    assert d["gpu_eager_bf16"]["c2"]["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert "full depth" in d["cpu_baseline"]["sample"]
+    assert d["warmup"] >= 3 and d["gpu_launches"] == d["gpu_launches_per_step"] * d["steps"] > 0
+    ref = json.loads([l for l in (ROOT / "profiles" / "r02_bench_reference_arm.json").read_text().splitlines()
+                      if l.startswith("{")][-1])
+    assert ref["impl"] == "reference" and ref["config"]["workload"] == d["config"]["workload"]
+    assert ref["ms_per_step"] * ref["cpu_baseline"]["steps_executed"] / 1e3 <= ref["wall_seconds"]
