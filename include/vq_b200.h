@@ -393,6 +393,23 @@ int vq_softmax_fwd(const float* scores, void* probs_bf16, int64_t rows, int32_t 
 /* dS = scale * P .* (dP - rowsum(dP .* P)) -> bf16 [rows, Tp]; with dropout, dP = mask * dprobs / (1-p) first. */
 int vq_softmax_bwd(const void* probs_bf16, const float* dprobs, void* dscores_bf16, int64_t rows, int32_t T,
                    int32_t ld_dprobs, int32_t Tp, float scale, const vq_dropout_desc* dropout, vq_stream_t stream);
+/* One-tile attention core of nn.MultiheadAttention(latents, context, context) (src/models/projector_perceiver.py:33,45)
+ * and its autograd backward (csrc/perceiver_attn.cu): one CTA per (sample, head), scores / dP never leave TMEM.
+ * Replaces S = q k^T | vq_softmax_fwd | P v (and dv | dP | vq_softmax_bwd | dq | dk backward) when num_latents is 64 or
+ * 128 and T <= 128, T % 8 == 0, head_dim % 64 == 0 (`vq_perceiver_attention_supported` says so; VQ_ERR_INVALID
+ * otherwise).  All bf16: q [B*Lq, E]; kv [B*T, 2E] = k | v; probs / probs_dropped [B*heads*Lq, Tp], Tp = T rounded up to
+ * 64 (columns T..Tp-1 = 0); att, datt, dq [B*Lq, E]; dkv [B*T, 2E] = dk | dv.  The scale is 1/sqrt(E/heads).  With dropout
+ * (site stream as in vq_softmax_fwd: row = (b*heads + h)*Lq + i, ld = Tp) probs_dropped receives mask * P / (1-p); the
+ * backward regenerates it from probs.  `vq_perceiver_attention_tune(0)` (or VQ_PERCEIVER_FUSED_ATTN=0) makes
+ * `_supported` answer 0, so that vq_perceiver_forward / _backward take the multi-launch formulation (A/B, debugging). */
+int vq_perceiver_attention_supported(int32_t Lq, int32_t T, int32_t E, int32_t heads);
+int vq_perceiver_attention_tune(int32_t fused);
+int vq_perceiver_attention_fwd(const void* q, const void* kv, void* probs, void* probs_dropped, void* att, int32_t B,
+                               int32_t heads, int32_t Lq, int32_t T, int32_t E, const vq_dropout_desc* dropout,
+                               vq_stream_t stream);
+int vq_perceiver_attention_bwd(const void* q, const void* kv, const void* probs, const void* datt, void* dq, void* dkv,
+                               int32_t B, int32_t heads, int32_t Lq, int32_t T, int32_t E,
+                               const vq_dropout_desc* dropout, vq_stream_t stream);
 /* LayerNorm backward (autograd of nn.LayerNorm at src/models/projector_perceiver.py:47,49): dz (bf16) from dy, the
  * saved LN input z and its row statistics; dgamma/dbeta (f32 [D]) are ACCUMULATED (+=).
  * With dropout, dz_dropped_bf16 additionally receives mask * dz / (1-p): the gradient of the branch that went through

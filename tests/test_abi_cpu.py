@@ -103,6 +103,15 @@ def test_new_entry_points_validate_arguments_without_gpu():
     assert b"step counts from 1" in h.vq_last_error()
     assert h.vq_splice_insert(None, 0, None, 8, None, None, None, None, 1, 8, 64, 4, None) == -1
     assert h.vq_find_first_token(None, 0, 0, None, None) == -1
+    # one-tile Perceiver attention: geometry is checked before anything touches the device
+    assert h.vq_perceiver_attention_supported(128, 128, 4096, 8) == 1
+    assert h.vq_perceiver_attention_supported(192, 128, 4096, 8) == 0
+    assert h.vq_perceiver_attention_fwd(None, None, None, None, None, 1, 8, 128, 128, 4096, None, None) == -1
+    assert b"null pointer" in h.vq_last_error()
+    assert h.vq_perceiver_attention_fwd(p, p, p, None, p, 1, 8, 128, 256, 4096, None, None) == -1
+    assert b"one-tile attention" in h.vq_last_error()
+    assert h.vq_perceiver_attention_bwd(p, p, p, p, p, p, 1, 8, 128, 128, 4096 + 8, None, None) == -1
+    assert b"head_dim" in h.vq_last_error()
 
 
 def test_host_wrappers_refuse_cpu_tensors():

@@ -213,6 +213,11 @@ _EXTRA_DECLS: dict[str, list] = {
     "vq_softmax_fwd": [_vp, _vp, _i64, _i32, _i32, _i32, C.POINTER(DropoutDesc), _vp, _vp],
     "vq_softmax_bwd": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, C.POINTER(DropoutDesc), _vp],
     "vq_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, C.POINTER(DropoutDesc), _vp, _vp],
+    "vq_perceiver_attention_supported": [_i32, _i32, _i32, _i32],
+    "vq_perceiver_attention_tune": [_i32],
+    "vq_perceiver_attention_fwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(DropoutDesc), _vp],
+    "vq_perceiver_attention_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(DropoutDesc),
+                                   _vp],
     "vq_dropout_mask": [_vp, _i64, _i32, _i32, C.POINTER(DropoutDesc), _vp],
     "vq_colsum": [_vp, _i32, _vp, _i64, _i32, _i64, _vp],
     "vq_cast_f32_bf16": [_vp, _vp, _i64, _vp],

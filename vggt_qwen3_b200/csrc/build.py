@@ -15,7 +15,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent
 LIB_PATH = CSRC.parent / "libvq_b200.so"
 STAMP = CSRC.parent / ".libvq_b200.stamp"
-SOURCES = ["common.cu", "gemm.cu", "attention.cu", "rowops.cu", "aggregator.cu", "perceiver_ops.cu", "perceiver.cu", "trainops.cu", "preprocess.cu", "geom.cu"]
+SOURCES = ["common.cu", "gemm.cu", "attention.cu", "rowops.cu", "aggregator.cu", "perceiver_ops.cu", "perceiver_attn.cu", "perceiver.cu", "trainops.cu", "preprocess.cu", "geom.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -189,6 +189,7 @@ extern "C" int vq_perceiver_forward(const vq_perceiver_cfg* c, const vq_perceive
   const Work k = carve_work(c, workspace);
   const int E = d.E, F = d.F, R = (int)d.R, C = (int)d.C;
   const float scale = 1.0f / sqrtf((float)d.hd);
+  const bool fused_attn = vq_perceiver_attention_supported(d.Lq, d.T, E, d.H) != 0;
 
   // context = in_proj(tokens); latents expanded over the batch
   RUN(gemm(st, C, E, c->in_dim, tokens, c->in_dim, 0, w->in_proj_w, c->in_dim, 0, s.ctx, E, VQ_BF16, w->in_proj_b));
@@ -201,31 +202,36 @@ extern "C" int vq_perceiver_forward(const vq_perceiver_cfg* c, const vq_perceive
     // q = lat Wq^T + bq ; kv = ctx [Wk;Wv]^T + [bk;bv]
     RUN(gemm(st, R, E, E, s.lat[l], E, 0, Wqkv, E, 0, L.q, E, VQ_BF16, lw.in_proj_b));
     RUN(gemm(st, C, 2 * E, E, s.ctx, E, 0, Wqkv + (size_t)E * E, E, 0, L.kv, 2 * E, VQ_BF16, lw.in_proj_b + E));
-    // scores[b,h] = scale * q[b,:,h] k[b,:,h]^T  -> f32 [A, Tp]
-    {
-      vq_gemm_desc g;
-      memset(&g, 0, sizeof(g));
-      g.M = d.Lq; g.N = d.T; g.K = d.hd;
-      g.Z0 = d.B; g.Z1 = d.H;
-      g.A = L.q; g.lda = E; g.a_r0 = d.Lq; g.a_c1 = d.hd; g.a_rows = R; g.a_cols = E;
-      g.B = L.kv; g.ldb = 2 * E; g.b_r0 = d.T; g.b_c1 = d.hd; g.b_rows = C; g.b_cols = E;
-      g.C = k.S; g.ldc = d.Tp; g.c_dtype = VQ_F32; g.c_r0 = (long long)d.H * d.Lq; g.c_r1 = d.Lq;
-      g.alpha = scale;
-      RUN(vq_gemm(&g, st));
-    }
     const vq_dropout_desc dr0 = site_of(c, l, 0), dr1 = site_of(c, l, 1), dr2 = site_of(c, l, 2), dr3 = site_of(c, l, 3);
-    RUN(vq_softmax_fwd(k.S, L.P, d.A, d.T, d.Tp, d.Tp, &dr0, L.Pd, st));
-    // att[b,:,h] = P[b,h] v[b,:,h]   (v is MN-major: keys along rows)
-    {
-      vq_gemm_desc g;
-      memset(&g, 0, sizeof(g));
-      g.M = d.Lq; g.N = d.hd; g.K = d.Tp;
-      g.Z0 = d.B; g.Z1 = d.H;
-      g.A = L.Pd; g.lda = d.Tp; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
-      g.B = reinterpret_cast<const __nv_bfloat16*>(L.kv) + E; g.ldb = 2 * E; g.b_major = 1;
-      g.b_r0 = d.T; g.b_c1 = d.hd; g.b_rows = C; g.b_cols = E;
-      g.C = L.att; g.ldc = E; g.c_dtype = VQ_BF16; g.c_r0 = d.Lq; g.c_c1 = d.hd;
-      RUN(vq_gemm(&g, st));
+    if (fused_attn) {
+      // one kernel per layer: S and P stay on chip (csrc/perceiver_attn.cu)
+      RUN(vq_perceiver_attention_fwd(L.q, L.kv, L.P, L.Pd, L.att, d.B, d.H, d.Lq, d.T, E, &dr0, st));
+    } else {
+      // scores[b,h] = scale * q[b,:,h] k[b,:,h]^T  -> f32 [A, Tp]
+      {
+        vq_gemm_desc g;
+        memset(&g, 0, sizeof(g));
+        g.M = d.Lq; g.N = d.T; g.K = d.hd;
+        g.Z0 = d.B; g.Z1 = d.H;
+        g.A = L.q; g.lda = E; g.a_r0 = d.Lq; g.a_c1 = d.hd; g.a_rows = R; g.a_cols = E;
+        g.B = L.kv; g.ldb = 2 * E; g.b_r0 = d.T; g.b_c1 = d.hd; g.b_rows = C; g.b_cols = E;
+        g.C = k.S; g.ldc = d.Tp; g.c_dtype = VQ_F32; g.c_r0 = (long long)d.H * d.Lq; g.c_r1 = d.Lq;
+        g.alpha = scale;
+        RUN(vq_gemm(&g, st));
+      }
+      RUN(vq_softmax_fwd(k.S, L.P, d.A, d.T, d.Tp, d.Tp, &dr0, L.Pd, st));
+      // att[b,:,h] = P[b,h] v[b,:,h]   (v is MN-major: keys along rows)
+      {
+        vq_gemm_desc g;
+        memset(&g, 0, sizeof(g));
+        g.M = d.Lq; g.N = d.hd; g.K = d.Tp;
+        g.Z0 = d.B; g.Z1 = d.H;
+        g.A = L.Pd; g.lda = d.Tp; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
+        g.B = reinterpret_cast<const __nv_bfloat16*>(L.kv) + E; g.ldb = 2 * E; g.b_major = 1;
+        g.b_r0 = d.T; g.b_c1 = d.hd; g.b_rows = C; g.b_cols = E;
+        g.C = L.att; g.ldc = E; g.c_dtype = VQ_BF16; g.c_r0 = d.Lq; g.c_c1 = d.hd;
+        RUN(vq_gemm(&g, st));
+      }
     }
     // z1 = lat + drop(att Wo^T + bo) ; x1 = LN1(z1)
     RUN(gemm(st, R, E, E, L.att, E, 0, lw.out_proj_w, E, 0, L.z1, E, VQ_BF16, lw.out_proj_b, s.lat[l], E, VQ_EPI_LINEAR,
@@ -258,6 +264,7 @@ extern "C" int vq_perceiver_backward(const vq_perceiver_cfg* c, const vq_perceiv
   const Work k = carve_work(c, workspace);
   const int E = d.E, F = d.F, R = (int)d.R, C = (int)d.C;
   const float scale = 1.0f / sqrtf((float)d.hd);
+  const bool fused_attn = vq_perceiver_attention_supported(d.Lq, d.T, E, d.H) != 0;
   const int acc = gr->accumulate;
 
   // wgrad: dW[N_out, K_in] (+)= dY^T X, both operands MN-major over the row (contraction) dimension; f32, or bf16
@@ -317,42 +324,46 @@ extern "C" int vq_perceiver_backward(const vq_perceiver_cfg* c, const vq_perceiv
     // attention core, per (sample, head)
     __nv_bfloat16* dkv = reinterpret_cast<__nv_bfloat16*>(k.dkv);
     const __nv_bfloat16* kv = reinterpret_cast<const __nv_bfloat16*>(L.kv);
-    {  // dV = Pd^T datt  -> dkv[:, E + h*hd]   (Pd = dropout(P), = P in eval mode)
-      vq_gemm_desc g;
-      memset(&g, 0, sizeof(g));
-      g.M = d.T; g.N = d.hd; g.K = d.Lq; g.Z0 = d.B; g.Z1 = d.H;
-      g.A = L.Pd; g.lda = d.Tp; g.a_major = 1; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
-      g.B = k.datt; g.ldb = E; g.b_major = 1; g.b_r0 = d.Lq; g.b_c1 = d.hd; g.b_rows = R; g.b_cols = E;
-      g.C = dkv + E; g.ldc = 2 * E; g.c_dtype = VQ_BF16; g.c_r0 = d.T; g.c_c1 = d.hd;
-      RUN(vq_gemm(&g, st));
-    }
-    {  // dP = datt v^T -> f32 [A, Tp]
-      vq_gemm_desc g;
-      memset(&g, 0, sizeof(g));
-      g.M = d.Lq; g.N = d.T; g.K = d.hd; g.Z0 = d.B; g.Z1 = d.H;
-      g.A = k.datt; g.lda = E; g.a_r0 = d.Lq; g.a_c1 = d.hd; g.a_rows = R; g.a_cols = E;
-      g.B = kv + E; g.ldb = 2 * E; g.b_r0 = d.T; g.b_c1 = d.hd; g.b_rows = C; g.b_cols = E;
-      g.C = k.S; g.ldc = d.Tp; g.c_dtype = VQ_F32; g.c_r0 = (long long)d.H * d.Lq; g.c_r1 = d.Lq;
-      RUN(vq_gemm(&g, st));
-    }
-    RUN(vq_softmax_bwd(L.P, k.S, k.dS, d.A, d.T, d.Tp, d.Tp, scale, &dr0, st));
-    {  // dq = dS k -> [R, E]
-      vq_gemm_desc g;
-      memset(&g, 0, sizeof(g));
-      g.M = d.Lq; g.N = d.hd; g.K = d.Tp; g.Z0 = d.B; g.Z1 = d.H;
-      g.A = k.dS; g.lda = d.Tp; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
-      g.B = kv; g.ldb = 2 * E; g.b_major = 1; g.b_r0 = d.T; g.b_c1 = d.hd; g.b_rows = C; g.b_cols = E;
-      g.C = k.dq; g.ldc = E; g.c_dtype = VQ_BF16; g.c_r0 = d.Lq; g.c_c1 = d.hd;
-      RUN(vq_gemm(&g, st));
-    }
-    {  // dk = dS^T q -> dkv[:, h*hd]
-      vq_gemm_desc g;
-      memset(&g, 0, sizeof(g));
-      g.M = d.T; g.N = d.hd; g.K = d.Lq; g.Z0 = d.B; g.Z1 = d.H;
-      g.A = k.dS; g.lda = d.Tp; g.a_major = 1; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
-      g.B = L.q; g.ldb = E; g.b_major = 1; g.b_r0 = d.Lq; g.b_c1 = d.hd; g.b_rows = R; g.b_cols = E;
-      g.C = dkv; g.ldc = 2 * E; g.c_dtype = VQ_BF16; g.c_r0 = d.T; g.c_c1 = d.hd;
-      RUN(vq_gemm(&g, st));
+    if (fused_attn) {
+      RUN(vq_perceiver_attention_bwd(L.q, L.kv, L.P, k.datt, k.dq, k.dkv, d.B, d.H, d.Lq, d.T, E, &dr0, st));
+    } else {
+      {  // dV = Pd^T datt  -> dkv[:, E + h*hd]   (Pd = dropout(P), = P in eval mode)
+        vq_gemm_desc g;
+        memset(&g, 0, sizeof(g));
+        g.M = d.T; g.N = d.hd; g.K = d.Lq; g.Z0 = d.B; g.Z1 = d.H;
+        g.A = L.Pd; g.lda = d.Tp; g.a_major = 1; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
+        g.B = k.datt; g.ldb = E; g.b_major = 1; g.b_r0 = d.Lq; g.b_c1 = d.hd; g.b_rows = R; g.b_cols = E;
+        g.C = dkv + E; g.ldc = 2 * E; g.c_dtype = VQ_BF16; g.c_r0 = d.T; g.c_c1 = d.hd;
+        RUN(vq_gemm(&g, st));
+      }
+      {  // dP = datt v^T -> f32 [A, Tp]
+        vq_gemm_desc g;
+        memset(&g, 0, sizeof(g));
+        g.M = d.Lq; g.N = d.T; g.K = d.hd; g.Z0 = d.B; g.Z1 = d.H;
+        g.A = k.datt; g.lda = E; g.a_r0 = d.Lq; g.a_c1 = d.hd; g.a_rows = R; g.a_cols = E;
+        g.B = kv + E; g.ldb = 2 * E; g.b_r0 = d.T; g.b_c1 = d.hd; g.b_rows = C; g.b_cols = E;
+        g.C = k.S; g.ldc = d.Tp; g.c_dtype = VQ_F32; g.c_r0 = (long long)d.H * d.Lq; g.c_r1 = d.Lq;
+        RUN(vq_gemm(&g, st));
+      }
+      RUN(vq_softmax_bwd(L.P, k.S, k.dS, d.A, d.T, d.Tp, d.Tp, scale, &dr0, st));
+      {  // dq = dS k -> [R, E]
+        vq_gemm_desc g;
+        memset(&g, 0, sizeof(g));
+        g.M = d.Lq; g.N = d.hd; g.K = d.Tp; g.Z0 = d.B; g.Z1 = d.H;
+        g.A = k.dS; g.lda = d.Tp; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
+        g.B = kv; g.ldb = 2 * E; g.b_major = 1; g.b_r0 = d.T; g.b_c1 = d.hd; g.b_rows = C; g.b_cols = E;
+        g.C = k.dq; g.ldc = E; g.c_dtype = VQ_BF16; g.c_r0 = d.Lq; g.c_c1 = d.hd;
+        RUN(vq_gemm(&g, st));
+      }
+      {  // dk = dS^T q -> dkv[:, h*hd]
+        vq_gemm_desc g;
+        memset(&g, 0, sizeof(g));
+        g.M = d.T; g.N = d.hd; g.K = d.Lq; g.Z0 = d.B; g.Z1 = d.H;
+        g.A = k.dS; g.lda = d.Tp; g.a_major = 1; g.a_r0 = (long long)d.H * d.Lq; g.a_r1 = d.Lq; g.a_rows = d.A; g.a_cols = d.Tp;
+        g.B = L.q; g.ldb = E; g.b_major = 1; g.b_r0 = d.Lq; g.b_c1 = d.hd; g.b_rows = R; g.b_cols = E;
+        g.C = dkv; g.ldc = 2 * E; g.c_dtype = VQ_BF16; g.c_r0 = d.T; g.c_c1 = d.hd;
+        RUN(vq_gemm(&g, st));
+      }
     }
     // projections: in_proj_weight.grad rows [0:E] <- q, rows [E:3E] <- k,v
     RUN(wgrad(lg.in_proj_w, E, E, k.dq, E, s.lat[l], E, R));

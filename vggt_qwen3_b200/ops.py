@@ -177,6 +177,55 @@ def dropout_mask(rows: int, cols: int, ld: int, p: float, seed: int, offset: int
     return keep
 
 
+def perceiver_attention_supported(num_latents: int, T: int, latent_dim: int, heads: int) -> bool:
+    """True when the Perceiver's attention core runs as the one-tile kernels (csrc/perceiver_attn.cu)."""
+    return bool(_lib.lib().vq_perceiver_attention_supported(num_latents, T, latent_dim, heads))
+
+
+def perceiver_attention_tune(fused: int = -1) -> None:
+    """0: vq_perceiver_forward / _backward take the multi-launch formulation (A/B, tests); 1: one-tile kernels."""
+    _lib.check(_lib.lib().vq_perceiver_attention_tune(fused), "vq_perceiver_attention_tune")
+
+
+def perceiver_attention_fwd(q: torch.Tensor, kv: torch.Tensor, B: int, heads: int,
+                            dropout: Optional["_lib.DropoutDesc"] = None):
+    """nn.MultiheadAttention's core for q [B*Lq, E], kv [B*T, 2E] = k | v (bf16): returns (att [B*Lq, E], probs
+    [B*heads*Lq, Tp], probs_dropped or None); one launch, scores stay in TMEM."""
+    _req(q, torch.bfloat16, "q")
+    _req(kv, torch.bfloat16, "kv")
+    assert q.dim() == 2 and kv.dim() == 2 and q.is_contiguous() and kv.is_contiguous()
+    E = q.shape[1]
+    assert kv.shape[1] == 2 * E and q.shape[0] % B == 0 and kv.shape[0] % B == 0
+    Lq, T = q.shape[0] // B, kv.shape[0] // B
+    Tp = (T + 63) // 64 * 64
+    probs = torch.empty(B * heads * Lq, Tp, device=q.device, dtype=torch.bfloat16)
+    dropped = torch.empty_like(probs) if dropout is not None and dropout.p > 0 else None
+    att = torch.empty_like(q)
+    _lib.check(_lib.lib().vq_perceiver_attention_fwd(q.data_ptr(), kv.data_ptr(), probs.data_ptr(), _ptr(dropped),
+                                                     att.data_ptr(), B, heads, Lq, T, E,
+                                                     C.byref(dropout) if dropout is not None else None, _stream()),
+               "vq_perceiver_attention_fwd")
+    return att, probs, dropped
+
+
+def perceiver_attention_bwd(q: torch.Tensor, kv: torch.Tensor, probs: torch.Tensor, datt: torch.Tensor, B: int,
+                            heads: int, dropout: Optional["_lib.DropoutDesc"] = None):
+    """Backward of `perceiver_attention_fwd`: (dq [B*Lq, E], dkv [B*T, 2E] = dk | dv), bf16, one launch."""
+    for t, n in ((q, "q"), (kv, "kv"), (probs, "probs"), (datt, "datt")):
+        _req(t, torch.bfloat16, n)
+        assert t.is_contiguous()
+    E = q.shape[1]
+    Lq, T = q.shape[0] // B, kv.shape[0] // B
+    assert datt.shape == q.shape and probs.shape == (B * heads * Lq, (T + 63) // 64 * 64)
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    _lib.check(_lib.lib().vq_perceiver_attention_bwd(q.data_ptr(), kv.data_ptr(), probs.data_ptr(), datt.data_ptr(),
+                                                     dq.data_ptr(), dkv.data_ptr(), B, heads, Lq, T, E,
+                                                     C.byref(dropout) if dropout is not None else None, _stream()),
+               "vq_perceiver_attention_bwd")
+    return dq, dkv
+
+
 def row_stats_cast(x: torch.Tensor, stats_zero: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(xb = bf16(x), stats f32 [rows, 2] = per-row (sum, sum of squares)) of an f32 [rows, D] tensor: the entry of a
     LayerNorm-folded GEMM chain (vq_gemm_desc.ln_stats); `stats_zero` (f32 [rows, 2]) is cleared in the same launch."""
