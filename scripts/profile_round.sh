@@ -19,11 +19,18 @@ for c in "gemm_fc1_gelu:gemm_kernel:gpu_bringup.py gemm_t_fc1_noaux" "gemm_fc2:g
          "gemm_proj:gemm_kernel:gpu_bringup.py gemm_t_proj_bf16" \
          "attn_bounded_frame8:attention_fwd_bounded:attn_case.py 8 1374 1" \
          "attn_bounded_global8x4:attention_fwd_bounded:attn_case.py 4 10992 1" \
-         "attn_checked_frame8:attention_fwd_wide:attn_case.py 8 1374 0"; do
+         "attn_checked_frame8:attention_fwd_wide:attn_case.py 8 1374 0" \
+         "pattn_fwd:perceiver_attn_fwd:pattn_case.py" "pattn_bwd:perceiver_attn_bwd:pattn_case.py"; do
   CASE=${c%%:*}; REST=${c#*:}; K=${REST%%:*}; CMD=${REST#*:}
   python scripts/$CMD > $O/${R}_${CASE}_plain.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o $O/${R}_${CASE} \
       python scripts/$CMD > $O/${R}_${CASE}_ncu.log 2>&1
   tail -1 $O/${R}_${CASE}_plain.log | cut -c1-160
+  # reduce on the box (gpurun merges at most 64 MiB back): text summary always, the report itself only for the first case
+  if [ -f $O/${R}_${CASE}.ncu-rep ]; then
+    python scripts/ncu_summary.py report $O/${R}_${CASE}.ncu-rep $O/${R}_${CASE}.txt > /dev/null 2>&1
+    [ "$CASE" = "gemm_fc1_gelu" ] || rm -f $O/${R}_${CASE}.ncu-rep
+  fi
 done
+python scripts/ncu_summary.py launches $O/${R}_launches.csv $O/${R}_launches_c2.txt > /dev/null 2>&1
 ls -la $O | grep ${R}_
