@@ -109,3 +109,27 @@ def test_uint8_views_equal_the_float_path_bit_for_bit():
         v = big[off:off + views.numel()].view(views.shape)
         v.copy_(views)
         assert torch.equal(agg.encode_tokens(v, None), b)
+
+
+@pytest.mark.parametrize("H,W,frames", [(518, 518, 3), (448, 448, 2), (126, 140, 1)])
+def test_uint8_patch_matrix_equals_the_float_one(H, W, frames):
+    """vq_im2col_patches_u8 (patch 14: raw byte strip in smem, 16-byte loads, table normalisation) against
+    vq_im2col_patches on ToTensor's float image: the same bf16 patch matrix bit for bit, for every alignment of the
+    view inside its buffer, including buffers that END with the last strip (no readable byte behind it)."""
+    from vggt_qwen3_b200 import _lib
+
+    lib = _lib.lib()
+    Kp, gh, gw = 592, H // 14, W // 14
+    views = torch.randint(0, 256, (frames, H, W, 3), generator=torch.Generator().manual_seed(H + frames), dtype=torch.uint8)
+    img = views.permute(0, 3, 1, 2).float().div(255).contiguous().cuda()
+    ref = torch.full((frames * gh * gw, Kp), 7.0, device="cuda", dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.vq_im2col_patches(img.data_ptr(), ref.data_ptr(), frames, H, W, 14, Kp, st), "im2col")
+    n = views.numel()
+    for off in (0, 1, 5, 8, 15):
+        big = torch.zeros(off + n, dtype=torch.uint8, device="cuda")      # the views end exactly at the buffer's end
+        big[off:].copy_(views.flatten())
+        out = torch.full_like(ref, -3.0)
+        _lib.check(lib.vq_im2col_patches_u8(big.data_ptr() + off, out.data_ptr(), frames, H, W, 14, Kp, st), "im2col_u8")
+        assert torch.equal(out, ref), f"offset {off}"
+    assert (ref[:, 588:] == 0).all()

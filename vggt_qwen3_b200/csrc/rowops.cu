@@ -89,6 +89,67 @@ im2col_kernel(const void* __restrict__ src, __nv_bfloat16* __restrict__ out, int
   }
 }
 
+// uint8 views with a compile-time patch size (14 for DINOv2 / VGGT): the byte strip of one patch row goes to smem RAW
+// with 16-byte loads (no per-byte index arithmetic), ToTensor + normalisation is a 3 x 256-entry table (the same IEEE
+// expression as above, evaluated once per CTA: bit-identical), and every thread assembles one 16-byte granule of a patch
+// row from (byte, table) lookups with constant divisors.
+template <int PS>
+__global__ void __launch_bounds__(256)
+im2col_u8_kernel(const unsigned char* __restrict__ src, __nv_bfloat16* __restrict__ out, int H, int W, int gh, int gw,
+                 int Kp) {
+  extern __shared__ __align__(16) unsigned char raw[];   // [16 slack][PS * W * 3 rounded up to 16][3 * 256 bf16]
+  const int f = blockIdx.x / gh, gy = blockIdx.x % gh;
+  const int nbytes = PS * W * 3;
+  const unsigned char* base = src + ((size_t)f * H + (size_t)gy * PS) * W * 3;
+  const int mis = (int)(reinterpret_cast<uintptr_t>(base) & 15);     // the strip starts `mis` bytes into a 16-byte line
+  const uint4* lines = reinterpret_cast<const uint4*>(base - mis);
+  const int nlines = (mis + nbytes + 15) >> 4;
+  __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(raw + ((PS * W * 3 + 31 + 15) & ~15));
+  // whole 16-byte lines: the first / last one may reach up to 15 bytes outside the strip -- still inside the frame
+  // buffer except at its very ends, where those lines are read bytewise
+  const bool head_ok = mis == 0 || f > 0 || gy > 0;
+  const bool tail_ok = ((mis + nbytes) & 15) == 0 || f + 1 < (int)(gridDim.x / gh) || gy + 1 < gh || H > gh * PS;
+  for (int i = threadIdx.x; i < nlines; i += blockDim.x) {
+    if ((i == 0 && !head_ok) || (i == nlines - 1 && !tail_ok)) {
+      for (int b = 0; b < 16; ++b) {
+        const int idx = 16 * i + b - mis;
+        if (idx >= 0 && idx < nbytes) raw[16 * i + b] = base[idx];
+      }
+    } else {
+      *reinterpret_cast<uint4*>(raw + 16 * i) = __ldg(lines + i);
+    }
+  }
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+    const int c = i >> 8;
+    const float mean = c == 0 ? 0.485f : c == 1 ? 0.456f : 0.406f;
+    const float istd = c == 0 ? 1.0f / 0.229f : c == 1 ? 1.0f / 0.224f : 1.0f / 0.225f;
+    lut[i] = __float2bfloat16(((float)(i & 255) / 255.0f - mean) * istd);
+  }
+  __syncthreads();
+  constexpr int K = 3 * PS * PS;
+  const int k8 = Kp / 8;
+  const int total = gw * k8;
+  const unsigned char* px = raw + mis;
+  __nv_bfloat16* dst = out + ((long long)f * gh + gy) * gw * Kp;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int gx = i / k8, k0 = (i - gx * k8) * 8;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      __nv_bfloat16 e = __float2bfloat16(0.f);
+      if (k < K) {
+        const int c = k / (PS * PS);
+        const int r = k - c * (PS * PS);
+        const int dy = r / PS, dx = r - dy * PS;
+        e = lut[c * 256 + px[(dy * W + gx * PS + dx) * 3 + c]];
+      }
+      v[j] = e;
+    }
+    *reinterpret_cast<uint4*>(dst + (long long)gx * Kp + k0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 // K3: rows 0..n_special-1 of every frame: cls + pos_embed[0], then the register tokens (f32 stream).
 __global__ void init_special_kernel(float* __restrict__ x, const float* __restrict__ cls,
                                     const float* __restrict__ pos0, const float* __restrict__ regs,
@@ -340,8 +401,19 @@ static int im2col_launch(const void* images, bool u8, void* out_bf16, int32_t fr
   LaunchScope scope(kKindRow, u8 ? "im2col_u8" : "im2col", frames, H, W, 0,
                     (double)frames * (3.0 * H * W * (u8 ? 1 : 4) + (double)gh * gw * Kp * 2), stream);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (u8) im2col_kernel<true><<<frames * gh, 256, smem, stream>>>(images, out, H, W, patch, gh, gw, Kp);
-  else im2col_kernel<false><<<frames * gh, 256, smem, stream>>>(images, out, H, W, patch, gh, gw, Kp);
+  if (u8 && patch == 14) {
+    // raw byte strip (+ up to 15 bytes either side of it) and the 3 x 256 normalisation table
+    const size_t smem14 = (((size_t)14 * W * 3 + 31 + 15) & ~(size_t)15) + 3 * 256 * sizeof(__nv_bfloat16);
+    VQ_CHECK_ARG(smem14 <= 200 * 1024, "image too wide for the im2col strip");
+    if (smem14 > 48 * 1024)
+      VQ_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(im2col_u8_kernel<14>), (int)smem14));
+    im2col_u8_kernel<14><<<frames * gh, 256, smem14, stream>>>(reinterpret_cast<const unsigned char*>(images), out, H, W,
+                                                               gh, gw, Kp);
+  } else if (u8) {
+    im2col_kernel<true><<<frames * gh, 256, smem, stream>>>(images, out, H, W, patch, gh, gw, Kp);
+  } else {
+    im2col_kernel<false><<<frames * gh, 256, smem, stream>>>(images, out, H, W, patch, gh, gw, Kp);
+  }
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
 }
