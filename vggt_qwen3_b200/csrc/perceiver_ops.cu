@@ -151,69 +151,98 @@ dropout_mask_kernel(uint8_t* __restrict__ keep, long long rows, int cols, int ld
   keep[i] = drop.thr ? (dropout_keep(drop, r, c, ld) ? 1 : 0) : 1;
 }
 
-// (2) dgamma[n] += sum_m dy*xhat, dbeta[n] += sum_m dy.  Each thread owns 8 adjacent columns (128-bit loads) and
-// walks a chunk of rows; one f32 atomic per column per CTA.  grid = (ceil(D/8/128), row chunks).
-__global__ void __launch_bounds__(128)
+// Column reductions over a chunk of rows.  CTA = 32 column groups (8 adjacent columns each: 128-bit loads, 512
+// contiguous bytes per row across the groups) x 8 row lanes; the 8 row lanes of a column meet in shared memory, so a CTA
+// issues ONE f32 atomic per column (the earlier one-thread-per-column-group version with 4-row chunks put 256 atomics
+// on every output address).  grid = (column slabs of 32 * kPer, row chunks).
+constexpr int kColGroups = 32, kRowLanes = 8;
+
+template <int NACC, int kPer>
+__device__ __forceinline__ void colreduce_finish(float (&acc)[NACC][kPer], float* __restrict__ const (&out)[NACC], int col0,
+                                                 int N) {
+  __shared__ float red[NACC][kRowLanes][kColGroups * kPer + 1];
+  const int cg = threadIdx.x % kColGroups, rl = threadIdx.x / kColGroups;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) red[a][rl][cg * kPer + j] = acc[a][j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < kColGroups * kPer; c += kColGroups * kRowLanes) {
+    if (col0 + c >= N) continue;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < kRowLanes; ++r) t += red[a][r][c];
+      atomicAdd(out[a] + col0 + c, t);
+    }
+  }
+}
+
+// (2) dgamma[n] += sum_m dy*xhat, dbeta[n] += sum_m dy
+__global__ void __launch_bounds__(kColGroups * kRowLanes)
 layernorm_bwd_affine_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
                             const float* __restrict__ mean, const float* __restrict__ rstd,
                             float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int D,
                             int rows_per_cta) {
-  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
-  if (col >= D) return;
+  const int cg = threadIdx.x % kColGroups, rl = threadIdx.x / kColGroups;
+  const int col0 = blockIdx.x * (kColGroups * 8);
+  const int col = col0 + cg * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = min(rows, r0 + rows_per_cta);
-  float ag[8], ab[8];
+  float acc[2][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = 0.f;
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (col < D) {
 #pragma unroll 4
-  for (long long r = r0; r < r1; ++r) {
-    const uint4 a = *reinterpret_cast<const uint4*>(dy + r * D + col);
-    const uint4 b = *reinterpret_cast<const uint4*>(z + r * D + col);
-    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
-    const float d[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y),
-                        bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
-    const float x[8] = {bf16_lo(b.x), bf16_hi(b.x), bf16_lo(b.y), bf16_hi(b.y),
-                        bf16_lo(b.z), bf16_hi(b.z), bf16_lo(b.w), bf16_hi(b.w)};
+    for (long long r = r0 + rl; r < r1; r += kRowLanes) {
+      const uint4 a = *reinterpret_cast<const uint4*>(dy + r * D + col);
+      const uint4 b = *reinterpret_cast<const uint4*>(z + r * D + col);
+      const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+      const float d[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y),
+                          bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
+      const float x[8] = {bf16_lo(b.x), bf16_hi(b.x), bf16_lo(b.y), bf16_hi(b.y),
+                          bf16_lo(b.z), bf16_hi(b.z), bf16_lo(b.w), bf16_hi(b.w)};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ag[j] += d[j] * (x[j] - mu) * rs;
-      ab[j] += d[j];
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += d[j] * (x[j] - mu) * rs;
+        acc[1][j] += d[j];
+      }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(dgamma + col + j, ag[j]);
-    atomicAdd(dbeta + col + j, ab[j]);
-  }
+  float* const outs[2] = {dgamma, dbeta};
+  colreduce_finish<2, 8>(acc, outs, col0, D);
 }
 
-// ---- out[n] += sum_m x[m, n]   (x bf16 or f32 [rows, N], out f32): 8 (bf16) / 4 (f32) columns per thread,
-// 128-bit loads, one atomic per column per CTA.  grid = (column slabs, row chunks)
+// ---- out[n] += sum_m x[m, n]   (x bf16 or f32 [rows, N], out f32): 8 (bf16) / 4 (f32) columns per thread
 template <bool F32>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kColGroups * kRowLanes)
 colsum_kernel(const void* __restrict__ x, float* __restrict__ out, long long rows, int N, long long ld,
               int rows_per_cta) {
   constexpr int kPer = F32 ? 4 : 8;
-  const int col = (blockIdx.x * 128 + threadIdx.x) * kPer;
-  if (col >= N) return;
+  const int cg = threadIdx.x % kColGroups, rl = threadIdx.x / kColGroups;
+  const int col0 = blockIdx.x * (kColGroups * kPer);
+  const int col = col0 + cg * kPer;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = min(rows, r0 + rows_per_cta);
-  float acc[kPer];
+  float acc[1][kPer];
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) acc[j] = 0.f;
+  for (int j = 0; j < kPer; ++j) acc[0][j] = 0.f;
+  if (col < N) {
 #pragma unroll 4
-  for (long long r = r0; r < r1; ++r) {
-    if constexpr (F32) {
-      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + r * ld + col);
-      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
-    } else {
-      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + r * ld + col);
-      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
-      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    for (long long r = r0 + rl; r < r1; r += kRowLanes) {
+      if constexpr (F32) {
+        const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + r * ld + col);
+        acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+      } else {
+        const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + r * ld + col);
+        acc[0][0] += bf16_lo(v.x); acc[0][1] += bf16_hi(v.x); acc[0][2] += bf16_lo(v.y); acc[0][3] += bf16_hi(v.y);
+        acc[0][4] += bf16_lo(v.z); acc[0][5] += bf16_hi(v.z); acc[0][6] += bf16_lo(v.w); acc[0][7] += bf16_hi(v.w);
+      }
     }
   }
-#pragma unroll
-  for (int j = 0; j < kPer; ++j) atomicAdd(out + col + j, acc[j]);
+  float* const outs[1] = {out};
+  colreduce_finish<1, kPer>(acc, outs, col0, N);
 }
 
 // ---- f32 -> bf16 cast, 8 elements per thread
@@ -348,12 +377,13 @@ extern "C" int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const f
   VQ_CHECK_CUDA(cudaGetLastError());
   {
     // enough CTAs to fill the machine: with 1024 rows x 4096 columns 32 rows per CTA gave 128 CTAs of 128 threads
-    const int col_ctas = (D / 8 + 127) / 128;
-    int rows_per_cta = 32;
-    while (rows_per_cta > 4 && (long long)col_ctas * ((rows + rows_per_cta - 1) / rows_per_cta) < 4LL * 148) rows_per_cta /= 2;
+    const int col_ctas = (D + kColGroups * 8 - 1) / (kColGroups * 8);
+    int rows_per_cta = 64;   // 8 rows per thread; fewer while the grid would not fill the machine twice over
+    while (rows_per_cta > 16 && (long long)col_ctas * ((rows + rows_per_cta - 1) / rows_per_cta) < 2LL * 148) rows_per_cta /= 2;
     dim3 grid(col_ctas, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
     LaunchScope scope(kKindRow, "layernorm_bwd_affine", (int)rows, D, 0, 0, (double)rows * D * 4.0, stream);
-    layernorm_bwd_affine_kernel<<<grid, 128, 0, stream>>>(dy, z, mean, rstd, dgamma, dbeta, rows, D, rows_per_cta);
+    layernorm_bwd_affine_kernel<<<grid, kColGroups * kRowLanes, 0, stream>>>(dy, z, mean, rstd, dgamma, dbeta, rows, D,
+                                                                            rows_per_cta);
   }
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
@@ -365,13 +395,13 @@ extern "C" int vq_colsum(const void* x, int32_t dtype, float* out, int64_t rows,
   VQ_CHECK_ARG(x && out && rows > 0 && N > 0 && ld >= N, "colsum arguments");
   VQ_CHECK_ARG(N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0, "colsum: 16-byte rows");
   const int per = dtype == VQ_F32 ? 4 : 8;
-  const int col_ctas = (N / per + 127) / 128;
-  int rows_per_cta = 32;   // fewer rows per CTA while the grid would not fill the machine (1024 x 4096: 128 CTAs at 32)
-  while (rows_per_cta > 4 && (long long)col_ctas * ((rows + rows_per_cta - 1) / rows_per_cta) < 4LL * 148) rows_per_cta /= 2;
+  const int col_ctas = (N + kColGroups * per - 1) / (kColGroups * per);
+  int rows_per_cta = 64;   // 8 rows per thread; fewer while the grid would not fill the machine twice over
+  while (rows_per_cta > 16 && (long long)col_ctas * ((rows + rows_per_cta - 1) / rows_per_cta) < 2LL * 148) rows_per_cta /= 2;
   dim3 grid(col_ctas, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
   LaunchScope scope(kKindRow, "colsum", (int)rows, N, 0, 0, (double)rows * N * (dtype == VQ_F32 ? 4.0 : 2.0), stream);
-  if (dtype == VQ_F32) colsum_kernel<true><<<grid, 128, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
-  else colsum_kernel<false><<<grid, 128, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
+  if (dtype == VQ_F32) colsum_kernel<true><<<grid, kColGroups * kRowLanes, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
+  else colsum_kernel<false><<<grid, kColGroups * kRowLanes, 0, stream>>>(x, out, rows, N, ld, rows_per_cta);
   VQ_CHECK_CUDA(cudaGetLastError());
   return VQ_OK;
 }
