@@ -141,6 +141,69 @@ layernorm_bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
   }
 }
 
+// Wide rows (D = 1024 * G8, G8 in {1, 2, 4, 8}): one CTA of 128 threads per row instead of one warp -- 8 x more threads in
+// flight for the B*Lq = 1024 rows of a c2 step, 128-bit loads, 8 * G8 elements per thread (one Philox call per 8-group).
+template <int G8, bool DROP>
+__global__ void __launch_bounds__(128)
+layernorm_bwd_dz_row_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                            const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dz, int D,
+                            const DropoutParams drop, __nv_bfloat16* __restrict__ dzd) {
+  __shared__ float red[2][4];
+  const long long r = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float mu = mean[r], rs = rstd[r];
+  float dyg[G8][8], xh[G8][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < G8; ++i) {
+    const int col = (i * 128 + threadIdx.x) * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(dy + r * D + col);
+    const uint4 b = *reinterpret_cast<const uint4*>(z + r * D + col);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dyg[i][2 * j] = bf16_lo(aw[j]) * gv[2 * j];
+      dyg[i][2 * j + 1] = bf16_hi(aw[j]) * gv[2 * j + 1];
+      xh[i][2 * j] = (bf16_lo(bw[j]) - mu) * rs;
+      xh[i][2 * j + 1] = (bf16_hi(bw[j]) - mu) * rs;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1 += dyg[i][j];
+      s2 += dyg[i][j] * xh[i][j];
+    }
+  }
+  s1 = wsum(s1);
+  s2 = wsum(s2);
+  if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+  __syncthreads();
+  s1 = (red[0][0] + red[0][1] + red[0][2] + red[0][3]) / D;
+  s2 = (red[1][0] + red[1][1] + red[1][2] + red[1][3]) / D;
+#pragma unroll
+  for (int i = 0; i < G8; ++i) {
+    const int col = (i * 128 + threadIdx.x) * 8;
+    uint32_t u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      u[j] = pack_bf16x2(rs * (dyg[i][2 * j] - s1 - xh[i][2 * j] * s2), rs * (dyg[i][2 * j + 1] - s1 - xh[i][2 * j + 1] * s2));
+    *reinterpret_cast<uint4*>(dz + r * D + col) = make_uint4(u[0], u[1], u[2], u[3]);
+    if (DROP && drop.thr) {
+      // gradient of the dropped branch: the mask acts on the bf16 dz the residual path sees
+      const uint32_t keep = dropout_keep8(drop, (uint64_t)r * (uint64_t)(D >> 3) + (uint64_t)(col >> 3));
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        w[j] = pack_bf16x2((keep >> (2 * j)) & 1u ? bf16_lo(u[j]) * drop.scale : 0.f,
+                           (keep >> (2 * j + 1)) & 1u ? bf16_hi(u[j]) * drop.scale : 0.f);
+      *reinterpret_cast<uint4*>(dzd + r * D + col) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
 // test hook: materialise a site's mask
 __global__ void __launch_bounds__(256)
 dropout_mask_kernel(uint8_t* __restrict__ keep, long long rows, int cols, int ld, const DropoutParams drop) {
@@ -361,6 +424,16 @@ extern "C" int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const f
   {
     const unsigned grid = (unsigned)((rows + 7) / 8);
     LaunchScope scope(kKindRow, "layernorm_bwd_dz", (int)rows, D, 0, 0, (double)rows * D * 6.0, stream);
+    const int g8 = D % 1024 == 0 ? D / 1024 : 0;
+    if (g8 == 1 || g8 == 2 || g8 == 4 || g8 == 8) {
+#define VQ_LNB_ROW(G)                                                                                                  \
+  case G:                                                                                                              \
+    if (drop.thr) layernorm_bwd_dz_row_kernel<G, true><<<(unsigned)rows, 128, 0, stream>>>(dy, z, mean, rstd, gamma, dz, D, drop, dzd); \
+    else layernorm_bwd_dz_row_kernel<G, false><<<(unsigned)rows, 128, 0, stream>>>(dy, z, mean, rstd, gamma, dz, D, drop, dzd); \
+    break;
+      switch (g8) { VQ_LNB_ROW(1) VQ_LNB_ROW(2) VQ_LNB_ROW(4) VQ_LNB_ROW(8) }
+#undef VQ_LNB_ROW
+    } else {
 #define VQ_LNB_CASE(V)                                                                                  \
   case V:                                                                                               \
     if (drop.thr) layernorm_bwd_dz_kernel<V, true><<<grid, 256, 0, stream>>>(dy, z, mean, rstd, gamma, dz, rows, D, drop, dzd); \
@@ -373,6 +446,7 @@ extern "C" int vq_layernorm_bwd(const void* dy_bf16, const void* z_bf16, const f
         return VQ_ERR_UNSUPPORTED;
     }
 #undef VQ_LNB_CASE
+    }
   }
   VQ_CHECK_CUDA(cudaGetLastError());
   {
