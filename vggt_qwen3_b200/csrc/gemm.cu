@@ -1007,19 +1007,19 @@ extern "C" int vq_gemm(const vq_gemm_desc* d, vq_stream_t stream_) {
   const int m_tiles = (d->M + kBlockM * cg - 1) / (kBlockM * cg);
   int block_n = 256;
   if (cg == 2 && d->N % 128 == 0 && d->K <= 1024) {
-    // Wave quantisation: a persistent grid of P pairs runs ceil(tiles / P) rounds.  256 x 128 tiles cost half a
-    // 256 x 256 tile plus ~8 % (A is re-read twice as often): take them when that is fewer tile-rounds overall
-    // (c2 proj: M = 10992, N = 1024 -> 172 tiles on 74 pairs = 3 rounds, against 5 half-rounds = 2.7).  Measured: a
-    // 5 % gain for K = 1024, a loss for K = 4096 (fc2), hence the K limit.
+    // 256 x 128 tiles only when 256 x 256 tiles would not even fill ONE round of the persistent grid (small M: the
+    // narrower tile doubles the number of busy pairs).  With more than one round the wide tile wins inside a step
+    // although the narrow one looks better alone: c2 proj (M = 10992, N = 1024: 172 tiles = 3 rounds against 5
+    // half-rounds) is 5 % faster in isolation with 128 and the whole c2 step 1.5 % SLOWER (A is re-read twice as often;
+    // at the power cap the extra L2 -> smem traffic costs clocks everywhere) -- `scripts/knob_sweep.sh`,
+    // profiles/r02_knob_sweep_in_step.txt.  K = 4096 (fc2) loses either way, hence the K limit.
     const long long pairs = (num_sms() > 1 ? num_sms() : 148) / 2;
     const long long t256 = (long long)m_tiles * ((d->N + 255) / 256), t128 = (long long)m_tiles * (d->N / 128);
-    const double cost256 = (double)((t256 + pairs - 1) / pairs);
-    const double cost128 = (double)((t128 + pairs - 1) / pairs) * 0.54;
     static const int force_bn = [] {
       const char* e = getenv("VQ_GEMM_BLOCK_N");
       return e ? atoi(e) : 0;
     }();
-    if (force_bn == 128 || (force_bn == 0 && cost128 < cost256)) block_n = 128;
+    if (force_bn == 128 || (force_bn == 0 && t256 <= pairs && t128 <= pairs)) block_n = 128;
   }
   if (cg == 1) {
     const long long tiles256 = (long long)m_tiles * ((d->N + 255) / 256) * Z0 * Z1;
