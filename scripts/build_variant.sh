@@ -6,7 +6,7 @@ sfx=$1; shift
 cd "$(dirname "$0")/.."
 objs=""
 mkdir -p vggt_qwen3_b200/build_$sfx
-for f in common gemm attention rowops aggregator perceiver_ops perceiver trainops preprocess geom; do
+for f in common gemm attention rowops aggregator perceiver_ops perceiver_attn perceiver trainops preprocess geom; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC "$@" \
        -c vggt_qwen3_b200/csrc/$f.cu -o vggt_qwen3_b200/build_$sfx/$f.o &
   objs="$objs vggt_qwen3_b200/build_$sfx/$f.o"

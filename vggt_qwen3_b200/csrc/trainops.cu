@@ -2,6 +2,8 @@
 //   f1  vq_splice_insert : the inference splice (src/inference/qa_inference.py:119-145), no host-side torch.cat
 //   f3  vq_adamw_step    : fused AdamW for the projector parameter group (src/train/train_sft.py:138-163,
 //                          torch.optim.AdamW defaults) that also refreshes the bf16 compute copy of the weights
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -223,7 +225,12 @@ static int adamw_launch(float* param, float* exp_avg, float* exp_avg_sq, const v
   const long long n4 = n / 4 > 0 ? n / 4 : 1;
   const int sms = num_sms() > 0 ? num_sms() : 148;
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 8LL * sms) blocks = 8LL * sms;   // grid-stride: 8 resident CTAs of 256 threads per SM
+  static const int ctas_per_sm = [] {   // grid-stride; 8 resident CTAs of 256 threads per SM unless overridden (tuning)
+    const char* e = getenv("VQ_ADAMW_CTAS_PER_SM");
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : v > 64 ? 64 : v;
+  }();
+  if (blocks > (long long)ctas_per_sm * sms) blocks = (long long)ctas_per_sm * sms;
   const double gbytes = grad_dtype == VQ_F32 ? 4.0 : 2.0, wbytes = !weight_out ? 0.0 : weight_dtype == VQ_F32 ? 4.0 : 2.0;
   LaunchScope scope(kKindRow, n_srcs > 1 ? "adamw_reduce_step" : "adamw_step", n_srcs, 0, 0, 0,
                     (double)n * (24.0 + gbytes * n_srcs + wbytes), stream);
