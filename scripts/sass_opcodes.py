@@ -22,7 +22,8 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             name = m.group(1)
-            cur = ("gemm_kernel" if "gemm_kernel" in name else "attention_fwd_bounded" if "attention_fwd_bounded" in name
+            cur = ("gemm_kernel" if "gemm_kernel" in name else "perceiver_attn (one-tile fwd / bwd)" if "perceiver_attn" in name
+                   else "attention_fwd_bounded" if "attention_fwd_bounded" in name
                    else "attention_fwd_wide" if "attention_fwd_wide" in name else "attention_fwd (split-KV)" if "attention_fwd" in name
                    else "row / elementwise kernels")
             fam[cur]["<kernels>"] += 1
