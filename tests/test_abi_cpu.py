@@ -126,3 +126,8 @@ def test_host_wrappers_refuse_cpu_tensors():
     p.grad = torch.ones(8)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         FusedAdamW([p], lr=1e-3).step()
+    q, kv = torch.zeros(128, 512, dtype=torch.bfloat16), torch.zeros(128, 1024, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.perceiver_attention_fwd(q, kv, 1, 4)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.perceiver_attention_bwd(q, kv, torch.zeros(512, 128, dtype=torch.bfloat16), q, 1, 4)
