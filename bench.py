@@ -215,6 +215,14 @@ def kernel_table(lib, n_steps: int, peaks: dict, profile_out, workload: str):
         if tr is not None:   # DRAM bytes per launch (read + write) from the committed ncu --set full capture
             roof.update({"traffic": tr["bytes"], "traffic_unit": "bytes/launch", "traffic_source": tr["source"],
                          "algorithmic_bytes": round(top["bytes"] / top["launches"])})
+    hbm_rows = [r for r in rows if r["kind"] == 2 and r["bytes"] > 0]
+    if roof is not None and hbm_rows:   # the memory-bound side of the step: its largest HBM-bound kernel against the copy peak
+        top = max(hbm_rows, key=lambda r: r["ms"])
+        gbs = top["bytes"] / top["ms"] / 1e6
+        roof["top_hbm_kernel"] = {"bound": "hbm", "kernel": f"{top['tag']}[{top['m']}x{top['n']}]", "achieved": round(gbs, 1),
+                                  "peak": peaks["hbm"], "unit": "GB/s", "frac": round(gbs / peaks["hbm"], 4),
+                                  "share_of_step": round(top["ms"] / total_ms, 4),
+                                  "avg_launch_us": round(1e3 * top["ms"] / top["launches"], 2)}
     return roof, breakdown
 
 
